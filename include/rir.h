@@ -1,0 +1,165 @@
+/*
+ * rir.h — C ABI of librir.so: the B200-native (sm_100a) retrieval hot path for
+ * Mak-GIBA/research_image_retrieval.
+ *
+ * The reference has NO native/FFI interface: its boundary is a set of Python
+ * call sites.  Each entry point below names the reference call
+ * (file:line under the reference's src/benchmark/) that it replaces.  A
+ * reference maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types in signatures;
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter is documented "host";
+ *   - the caller owns every buffer; the library never allocates device memory —
+ *     scratch space is sized by the *_workspace() query and passed in;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream);
+ *   - return value: RIR_OK (0) or a negative RIR_E_* code; rir_last_error()
+ *     returns a thread-local human readable message for the last failure;
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x
+ *     every launching entry point returns RIR_E_ARCH.
+ */
+#ifndef RIR_H_
+#define RIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIR_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define RIR_OK 0
+#define RIR_E_ARG (-1)       /* bad argument (shape / alignment / dtype)            */
+#define RIR_E_ARCH (-2)      /* current device is not sm_100 (B200)                 */
+#define RIR_E_CUDA (-3)      /* a CUDA runtime / driver call failed                 */
+#define RIR_E_WORKSPACE (-4) /* workspace too small for the requested problem       */
+
+/* element types of descriptor / feature-map storage */
+#define RIR_F32 0
+#define RIR_BF16 1
+#define RIR_FP8E4M3 2
+
+/* pooling modes */
+#define RIR_POOL_GEM 0 /* (mean_hw max(x,eps)^p)^(1/p)   networks/RetrievalNet.py:318-325 */
+#define RIR_POOL_MAX 1 /* max_hw x (MAC)                 models/spoc.py:12-49 level 1     */
+#define RIR_POOL_AVG 2 /* mean_hw max(x,eps) (SPoC)      networks/RetrievalNet.py:359-365 */
+
+/* rir_sim_topk path selection */
+#define RIR_PATH_AUTO 0
+#define RIR_PATH_STREAM 1 /* TMA-bulk ring + CUDA-core dot products (tiny query batches) */
+#define RIR_PATH_MMA 2    /* tcgen05 tensor-core contraction, TMEM accumulators          */
+#define RIR_PATH_EXACT 3  /* one-CTA-per-query robust scan (overflow fallback; slow)     */
+
+/* per-(protocol,query) status written by rir_revisited_map / rir_compute_map */
+#define RIR_MAP_OK 0
+#define RIR_MAP_EMPTY_OK 1         /* no positives for this query: ap=+inf, excluded (utils/evaluate.py:65-68) */
+#define RIR_MAP_NO_POS_RETRIEVED 2 /* positives exist, none in the ranked list: ap=0; with kappas the reference
+                                      raises ValueError at utils/evaluate.py:101 — the host shim re-raises       */
+
+int rir_version(void);
+const char* rir_last_error(void);
+/* RIR_OK iff the current device is compute capability 10.x. */
+int rir_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Descriptor build: pooling -> L2 -> whitening -> L2 -> multi-scale aggregate
+ * ------------------------------------------------------------------------------------------ */
+
+/* Global spatial pooling of feature maps x[B,C,HW] (NCHW contiguous, HW = H*W) to out[B,C] fp32.
+ * Replaces gem.forward (networks/RetrievalNet.py:318-325), GeMPooling.forward (models/gem_pooling.py:12-23),
+ * G2Pooling.forward (models/senet_g2.py:132-153: out = alpha*gem + beta), AttentionBasedGlobalPooling.gem_pooling
+ * (models/ultron_modules/ultron.py:193-205), spoc.forward (networks/RetrievalNet.py:359-365) and the level-1 max
+ * pool of SpatialPyramidPooling (models/spoc.py:33-35).  dtype in {RIR_F32, RIR_BF16}.  alpha=1,beta=0 for plain GeM. */
+int rir_pool(const void* x, int dtype, int B, int C, int HW, int mode, float p, float eps, float alpha, float beta,
+             float* out, void* stream);
+
+/* Row-wise L2 normalisation out[i,:] = x[i,:] / max(||x[i,:]||_2, eps); in-place allowed.
+ * Replaces F.normalize(x, p=2, dim=-1) at networks/RetrievalNet.py:343,587,589, networks/spca.py:65,
+ * models/gem_pooling.py:91, iris_evaluate.py:379-380 (torch default eps = 1e-12). */
+int rir_l2_normalize(const float* x, int64_t n_rows, int d, float eps, float* out, void* stream);
+
+/* Whitening / dimensionality reduction out[B,d_out] = x[B,C] * W[d_out,C]^T + bias, fp32 accumulate.
+ * Replaces the 1x1 Conv2d / Linear `self.whiten` (networks/RetrievalNet.py:332,342,577,588; networks/spca.py:31-46,61-64)
+ * with weights produced by ConvDimReduction.initialize_pca_whitening (networks/spca.py:215-227). bias may be NULL.
+ * If l2_after != 0 each output row is L2-normalised (eps 1e-12) in the same launch sequence. */
+int rir_whiten(const float* x, const float* W, const float* bias, int B, int C, int d_out, int l2_after, float* out,
+               void* stream);
+
+/* Multi-scale aggregation of extract_vectors (utils/helpfunc.py:31-44): v[N,S,D] per-scale descriptors,
+ * keep[N,S] (1 = scale used, 0 = dropped because the resized image was < 36 px; NULL = all kept);
+ * out[n,:] = L2( sum_s keep*v[n,s,:] / #kept ). */
+int rir_scale_mean_l2(const float* v, const uint8_t* keep, int64_t N, int S, int D, float* out, void* stream);
+
+/* Cast fp32 descriptors v[n,d] into the database layout sim_topk reads: row-major bf16, or fp8 e4m3 with a
+ * per-row fp32 scale (row = scale * fp8).  (The reference keeps descriptors as fp32 torch tensors:
+ * utils/helpfunc.py:21,27 — this is the B200 storage format for them.)  scale_out ignored for bf16. */
+int rir_pack_descriptors(const float* v, int64_t n, int d, int dtype_out, void* out, float* scale_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Search: similarity + top-k (never materialises the [nq, n] score matrix)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of scratch rir_sim_topk needs for this problem (0 on invalid arguments). */
+size_t rir_sim_topk_workspace(int nq, int64_t n_local, int d, int k, int dtype);
+
+/* Exact top-k of S = Q X^T per query, descending score, ties -> ascending index.
+ * Replaces torch.mm(q, g.t()) + np.argsort(-sim, axis=1) (iris_evaluate.py:383-386) and
+ * compute_similarity + torch.topk (reference/manus/7_AdaptiveHybridModel/modified/
+ * adaptive_hybrid_retrieval_complete.py:11-16,428).
+ *   Q[nq,d], X[n_local,d] row-major, dtype in {RIR_BF16, RIR_FP8E4M3, RIR_F32}; d*elemsize % 16 == 0, 16-byte aligned
+ *   bases.  RIR_F32 keeps the reference's fp32 arithmetic (CUDA-core stream path only, for ROxford/RParis-size sets);
+ *   q_scale[nq], x_scale[n_local]: per-row dequantisation scales (NULL = 1);
+ *   1 <= k <= n_local; k <= 8192, or any k <= n_local when n_local <= 16384 (k == n_local yields the full ranking);
+ *   idx_offset is added to every returned row index (global index of shard row 0);
+ *   out_score[nq,k] fp32, out_idx[nq,k] int32. */
+int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                 int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
+                 void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* k-way merge of G per-shard top-k lists sc/ix[G,nq,k] (as produced by an allgather of rir_sim_topk outputs)
+ * into the global top-k (same order rule).  No reference counterpart. */
+size_t rir_merge_topk_workspace(int G, int nq, int k);
+int rir_merge_topk(const float* sc, const int32_t* ix, int G, int nq, int k, float* out_sc, int32_t* out_ix,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* alpha query expansion (skeleton reference/manus/1_SPARSE/sparse_model.py:374-405):
+ *   acc[q,:] (+)= sum_{j<kq, idx_off <= ix[q,j] < idx_off+n_local} max(sc[q,j],0)^alpha * dequant(X[ix[q,j]-idx_off,:])
+ * accumulates the contribution of the rows this shard owns (acc fp32 [nq,d], zero it first; all-reduce across shards). */
+int rir_aqe_accumulate(const void* X, int dtype, const float* x_scale, int64_t n_local, int64_t idx_offset, int d,
+                       const float* sc, const int32_t* ix, int nq, int ld_topk, int kq, float alpha, float* acc,
+                       void* stream);
+/* q'[q,:] = L2(dequant(Q[q,:]) + acc[q,:]); written as fp32 (out_f32, may be NULL) and in the search dtype
+ * (out_q + out_scale, may be NULL). */
+int rir_aqe_finalize(const void* Q, int dtype, const float* q_scale, const float* acc, int nq, int d, float* out_f32,
+                     void* out_q, float* out_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Revisited-protocol evaluation
+ * ------------------------------------------------------------------------------------------ */
+
+/* Junk-aware mAP and P@k for P protocols in one launch.
+ * Replaces compute_ap / compute_map (utils/evaluate.py:4-34, 37-150; duplicate iris_evaluate.py:11-187).
+ *   ranks[nq, L] int32, row q = ranked db ids of query q (best first), -1 = padding (truncated / ragged lists);
+ *   ld = row stride in elements (>= L).  (The reference layout is ranks[L, nq]; the host shim transposes.)
+ *   Three sorted id lists per query in CSR form: lists A, B, C (x_ids = concatenated ids, x_off[nq+1] = offsets;
+ *   a NULL list is empty).
+ *   proto[P] selects membership per protocol p: bits 0-2 = lists whose union is `ok`, bits 4-6 = lists whose
+ *   union is `junk` (bit0/4 = A, bit1/5 = B, bit2/6 = C).  Revisited protocols (utils/evaluate.py:163-185) with
+ *   A=easy, B=hard, C=junk:  Easy 0x61 (ok=A, junk=C|B), Medium 0x43 (ok=A|B, junk=C), Hard 0x52 (ok=B, junk=C|A).
+ *   kappas[nk] int32 (nk may be 0).  proto and kappas are small HOST arrays (copied into the launch parameters).
+ * Outputs (fp64, identical operation order to the reference's Python floats):
+ *   map[P], aps[P,nq] (+inf for empty ok), mpr[P,nk], prs[P,nq,nk], status[P,nq] (RIR_MAP_*). */
+int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t ld, const int32_t* a_ids, const int32_t* a_off,
+                    const int32_t* b_ids, const int32_t* b_off, const int32_t* c_ids, const int32_t* c_off,
+                    const int32_t* proto, int P, const int32_t* kappas, int nk, double* map, double* aps, double* mpr,
+                    double* prs, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIR_H_ */

@@ -1,0 +1,17 @@
+"""research_image_retrieval_b200 — the B200-native retrieval hot path of Mak-GIBA/research_image_retrieval.
+
+pool -> L2 -> whiten -> L2 -> Q·Xᵀ -> top-k -> alpha-QE -> revisited mAP, as PyTorch host code over the C ABI of
+librir.so (include/rir.h), which launches hand-written sm_100a kernels.  No Triton, no dispatcher, no CPU fallback.
+
+The module names mirror the reference's (`src/benchmark/utils/{evaluate,helpfunc}.py`, `networks/`), so a caller
+switches with an import change — see INTEGRATION.md.
+"""
+from ._lib import LIB_PATH, RirError, load  # noqa: F401
+from .evaluate import compute_ap, compute_map, compute_map_and_print, revisited_map  # noqa: F401
+from .helpfunc import extract_vectors, scale_mean_l2  # noqa: F401
+from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, gem, gem_pool, l2n, mac_pool, spoc,  # noqa: F401
+                      spoc_pool, ultron_gem_pooling, whiten)
+from .search import (Database, ShardedDatabase, alpha_query_expansion, merge_topk, pack_descriptors, rank,  # noqa: F401
+                     search_with_aqe, shard_bounds, sim_topk)
+
+__version__ = "0.1.0"

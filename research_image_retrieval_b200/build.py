@@ -1,0 +1,106 @@
+"""Build librir.so (sm_100a only) in-tree with nvcc.
+
+`python -m research_image_retrieval_b200.build` (or `__graft_entry__.build()`) compiles every .cu under csrc/ into
+`research_image_retrieval_b200/lib/librir.so`.  nvcc cross-compiles without a GPU.  The .so is git-ignored but travels
+with the tree to the GPU box.  No JIT, no torch extension machinery: the product boundary is the plain C ABI of
+include/rir.h, loaded with ctypes (see _lib.py).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "librir.so")
+
+SOURCES = [
+    "rir_api.cu",
+    "descriptor_build.cu",
+    "sim_topk_stream.cu",
+    "sim_topk_mma.cu",
+    "sim_topk_select.cu",
+    "query_expansion.cu",
+    "evaluate_map.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: librir.so cannot be built (there is no CPU fallback)")
+    return cand
+
+
+def _digest(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        with open(p, "rb") as f:
+            h.update(p.encode())
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _inputs():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "rir.h"))
+    return files
+
+
+def is_current() -> bool:
+    stamp = LIB + ".sha256"
+    if not (os.path.exists(LIB) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as f:
+        return f.read().strip() == _digest(_inputs())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link librir.so; returns its path.  Skips the work when sources are unchanged."""
+    if not force and is_current():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = os.path.join(OBJDIR, src.replace(".cu", ".ptxas.log"))
+        with open(log, "w") as f:
+            f.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(LIB + ".sha256", "w") as f:
+        f.write(_digest(_inputs()))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

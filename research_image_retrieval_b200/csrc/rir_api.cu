@@ -1,0 +1,227 @@
+// rir_api.cu — C-ABI glue: error state, device checks and the sim_topk orchestration
+// (sample -> threshold -> scan -> select -> overflow fallback; see sim_topk.cuh).
+#include <stdarg.h>
+#include <string.h>
+#include "sim_topk.cuh"
+#include "topk_select.cuh"
+
+namespace rir {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_arch_ok[64];   // 0 unknown, 1 ok, -1 bad
+static int g_sm_count[64];
+
+int check_arch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available: librir.so has no CPU fallback");
+    return RIR_E_ARCH;
+  }
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (g_arch_ok[dev] == 0) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaGetDeviceProperties failed");
+      return RIR_E_ARCH;
+    }
+    g_sm_count[dev] = prop.multiProcessorCount;
+    g_arch_ok[dev] = (prop.major == 10) ? 1 : -1;
+    if (g_arch_ok[dev] < 0)
+      set_error("device %d is sm_%d%d; librir.so is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+  }
+  if (g_arch_ok[dev] < 0) {
+    set_error("current device is not sm_100 (B200); librir.so has no fallback path");
+    return RIR_E_ARCH;
+  }
+  return RIR_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sim_topk planning (host): sample size, candidate capacity, workspace carve-up
+// ---------------------------------------------------------------------------------------------
+constexpr int kQueryGroup = 4096;      // queries processed per internal pass (bounds the workspace)
+constexpr long long kScanAllMaxRows = 16384;
+constexpr int kMaxKFilter = 8192;
+constexpr int kMaxK = 16384;
+
+struct SimPlan {
+  bool scan_all;
+  int nblk, sblk, cap;
+  int group;  // queries per pass
+  size_t off_tau_s, off_tau_i, off_cnt, off_ovf, off_sample, off_cand, total;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
+  if (nq < 0 || n < 1 || k < 1 || k > kMaxK || k > n) return false;
+  pl->nblk = (int)((n + kSampleBlockRows - 1) / kSampleBlockRows);
+  pl->group = nq < kQueryGroup ? (nq < 1 ? 1 : nq) : kQueryGroup;
+  if (n <= kScanAllMaxRows) {
+    pl->scan_all = true;
+    pl->sblk = 0;
+    pl->cap = (int)align_up((size_t)n, 32);
+  } else {
+    if (k > kMaxKFilter) return false;
+    pl->scan_all = false;
+    long long sblk = (long long)(0.02 * pl->nblk + 0.5);
+    if (sblk < 74) sblk = 74;                        // half a wave of 256-row tiles
+    const long long need = (4ll * k + kSampleBlockRows - 1) / kSampleBlockRows;
+    if (sblk < need) sblk = need;
+    if (sblk > pl->nblk - 1) sblk = pl->nblk - 1;    // the last block may be partial: never sample it
+    pl->sblk = (int)sblk;
+    const double expected = (double)k * (double)n / ((double)sblk * kSampleBlockRows);
+    long long cap = pow2_ceil_int((int)(3.0 * expected) + 1024);
+    if (cap < 2048) cap = 2048;
+    pl->cap = (int)cap;
+  }
+  const size_t g = (size_t)align_up((size_t)pl->group, 128);
+  size_t o = 0;
+  pl->off_tau_s = o; o = align_up(o + g * 4, 256);
+  pl->off_tau_i = o; o = align_up(o + g * 4, 256);
+  pl->off_cnt = o;   o = align_up(o + g * 4, 256);
+  pl->off_ovf = o;   o = align_up(o + g * 4, 256);
+  pl->off_sample = o; o = align_up(o + g * (size_t)pl->sblk * kSampleBlockRows * 4, 256);
+  pl->off_cand = o;  o = align_up(o + g * (size_t)pl->cap * 8, 256);
+  pl->total = o;
+  return true;
+}
+
+}  // namespace rir
+
+using namespace rir;
+
+extern "C" int rir_version(void) { return RIR_VERSION; }
+extern "C" const char* rir_last_error(void) { return g_err; }
+extern "C" int rir_device_check(void) { return check_arch(); }
+
+static int elem_size(int dtype) { return dtype == RIR_BF16 ? 2 : (dtype == RIR_FP8E4M3 ? 1 : (dtype == RIR_F32 ? 4 : 0)); }
+
+extern "C" size_t rir_sim_topk_workspace(int nq, int64_t n_local, int d, int k, int dtype) {
+  SimPlan pl;
+  if (elem_size(dtype) == 0 || d < 1) return 0;
+  long long kk = k;
+  if (kk > n_local) kk = n_local;  // the tail is padded with (-inf, -1)
+  if (!make_plan(nq, n_local, (int)kk, &pl)) return 0;
+  return pl.total;
+}
+
+extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale,
+                            int nq, int64_t n_local, int d, int k, int64_t idx_offset, float* out_score,
+                            int32_t* out_idx, void* workspace, size_t workspace_bytes, int path, void* stream) {
+  if (int e = check_arch()) return e;
+  const int esz = elem_size(dtype);
+  RIR_REQUIRE(esz != 0, "sim_topk: dtype must be RIR_F32, RIR_BF16 or RIR_FP8E4M3 (got %d)", dtype);
+  RIR_REQUIRE(dtype != RIR_F32 || path != RIR_PATH_MMA, "sim_topk: fp32 descriptors run on the stream path only");
+  RIR_REQUIRE(nq >= 0 && n_local >= 0 && d >= 1 && k >= 1, "sim_topk: bad shape nq=%d n=%lld d=%d k=%d", nq,
+              (long long)n_local, d, k);
+  RIR_REQUIRE(k <= kMaxK, "sim_topk: k=%d exceeds %d", k, kMaxK);
+  RIR_REQUIRE(((size_t)d * esz) % 16 == 0, "sim_topk: row size %zu B must be a multiple of 16 (pad d with zeros)",
+              (size_t)d * esz);
+  RIR_REQUIRE(out_score && out_idx, "sim_topk: null output");
+  RIR_REQUIRE(n_local + idx_offset < (1ll << 31) && idx_offset >= 0, "sim_topk: global row index exceeds int32");
+  RIR_REQUIRE(path >= RIR_PATH_AUTO && path <= RIR_PATH_EXACT, "sim_topk: bad path %d", path);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nq == 0) return RIR_OK;
+  RIR_REQUIRE(Q, "sim_topk: null Q");
+  RIR_REQUIRE((reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+              "sim_topk: Q and X must be 16-byte aligned");
+
+  RIR_REQUIRE(X, "sim_topk: null X");
+  RIR_REQUIRE(n_local >= 1, "sim_topk: empty shard (n_local == 0) - give every rank at least one row");
+  RIR_REQUIRE(k <= n_local, "sim_topk: k=%d exceeds the shard size %lld (clamp k on the host)", k, (long long)n_local);
+
+  SimPlan pl;
+  if (!make_plan(nq, n_local, k, &pl)) {
+    set_error("sim_topk: unsupported combination k=%d n=%lld (k <= %d, or n <= %lld for a full ranking)", k,
+              (long long)n_local, kMaxKFilter, kScanAllMaxRows);
+    return RIR_E_ARG;
+  }
+  if (path == RIR_PATH_EXACT) {
+    SimParams p{};
+    p.Q = Q; p.X = X; p.q_scale = q_scale; p.x_scale = x_scale;
+    p.nq = nq; p.q0 = 0; p.n = n_local; p.d = d; p.row_bytes = d * esz;
+    return launch_exact_scan(p, dtype, nq, k, idx_offset, out_score, out_idx, nullptr, st);
+  }
+  RIR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "sim_topk: workspace must be non-null and 256-byte aligned");
+  if (workspace_bytes < pl.total) {
+    set_error("sim_topk: workspace of %zu B is smaller than the required %zu B", workspace_bytes, pl.total);
+    return RIR_E_WORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+
+  for (int g0 = 0; g0 < nq; g0 += pl.group) {
+    const int gq = (nq - g0) < pl.group ? (nq - g0) : pl.group;
+    SimParams p{};
+    p.Q = reinterpret_cast<const uint8_t*>(Q) + (size_t)g0 * d * esz;
+    p.X = X;
+    p.q_scale = q_scale ? q_scale + g0 : nullptr;
+    p.x_scale = x_scale;
+    p.n = n_local; p.d = d; p.row_bytes = d * esz;
+    p.nblk = pl.nblk; p.sblk = pl.sblk;
+    p.sample_scores = reinterpret_cast<float*>(ws + pl.off_sample);
+    p.tau_score = reinterpret_cast<float*>(ws + pl.off_tau_s);
+    p.tau_idx = reinterpret_cast<uint32_t*>(ws + pl.off_tau_i);
+    p.cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+    p.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
+    p.cap = pl.cap;
+    uint32_t* ovf = reinterpret_cast<uint32_t*>(ws + pl.off_ovf);
+    const bool use_stream = (path == RIR_PATH_STREAM) || dtype == RIR_F32 || (path == RIR_PATH_AUTO && gq <= 4);
+
+    auto run_pass = [&](int mode) -> int {
+      p.mode = mode;
+      if (use_stream) {
+        for (int s0 = 0; s0 < gq; s0 += 8) {  // the stream kernel holds <= 8 queries in shared memory
+          p.q0 = s0;
+          p.nq = (gq - s0) < 8 ? (gq - s0) : 8;
+          if (int e = launch_sim_stream(p, dtype, st)) return e;
+        }
+        p.q0 = 0;
+        p.nq = gq;
+        return RIR_OK;
+      }
+      p.q0 = 0;
+      p.nq = gq;
+      return launch_sim_mma(p, dtype, st);
+    };
+
+    p.nq = gq;
+    if (pl.scan_all) {
+      // every row is a candidate: slot == row, cnt = n set by the select kernel's launch parameters
+      if (int e = run_pass(kModeScanAll)) return e;
+      p.mode = kModeScanAll;
+    } else {
+      if (int e = run_pass(kModeSample)) return e;
+      if (int e = launch_sample_threshold(p, gq, k, st)) return e;
+      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (size_t)gq * sizeof(uint32_t), st));
+      if (int e = run_pass(kModeScanFilter)) return e;
+      p.mode = kModeScanFilter;
+    }
+    float* os = out_score + (size_t)g0 * k;
+    int32_t* oi = out_idx + (size_t)g0 * k;
+    if (int e = launch_final_select(p, gq, k, idx_offset, os, oi, ovf, st)) return e;
+    if (!pl.scan_all) {
+      // queries whose candidate list overflowed (adversarial row order) are redone exactly; no-op otherwise
+      if (int e = launch_exact_scan(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
+    }
+  }
+  return RIR_OK;
+}

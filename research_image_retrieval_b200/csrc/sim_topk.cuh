@@ -1,0 +1,70 @@
+// sim_topk.cuh — parameters shared by the similarity + top-k kernels.
+//
+// Replaces torch.mm(q, g.t()) + np.argsort / torch.topk (iris_evaluate.py:383-386;
+// reference/manus/7_AdaptiveHybridModel/modified/adaptive_hybrid_retrieval_complete.py:11-16,428)
+// without ever writing the [nq, n] score matrix to HBM.
+//
+// Scheme (exact):
+//   1. SAMPLE pass  : score `sblk` strided 256-row blocks of the shard densely -> sample_scores[nq, sblk*256].
+//   2. threshold    : tau[q] = k-th best (score, index) key of the sample.  The sample is a subset of the shard, so
+//                     tau[q] <= the true k-th best key: filtering with it can never drop a top-k row.
+//   3. SCAN pass    : score every row once; rows whose key >= tau[q] are appended to cand[q, cap] (rare: ~k*n/S).
+//   4. final select : exact top-k of cand[q] (radix select + bitonic sort) -> out.
+//   5. fallback     : a query whose candidate list overflowed `cap` (adversarial row order) is re-done by the
+//                     one-CTA-per-query exact kernel.  Small shards (n <= cap) skip 1-2 and push every row.
+#pragma once
+#include "rir_common.cuh"
+
+namespace rir {
+
+constexpr int kSampleBlockRows = 256;  // rows per sample block == MMA tile N
+
+enum SimMode : int { kModeScanFilter = 0, kModeSample = 1, kModeScanAll = 2 };
+
+struct SimParams {
+  const void* Q;         // [nq, d]
+  const void* X;         // [n, d]
+  const float* q_scale;  // [nq] or nullptr
+  const float* x_scale;  // [n]  or nullptr
+  int nq;                // queries handled by this launch (<= 128 per MMA query block; any for select kernels)
+  int q0;                // first query of this launch (offset into Q / tau / cnt / cand / sample_scores rows)
+  long long n;           // rows in this shard
+  int d;
+  int row_bytes;         // d * sizeof(element)
+  int mode;              // SimMode
+  int nblk;              // ceil(n / 256)
+  int sblk;              // sample blocks (<= nblk)
+  float* sample_scores;  // [nq_total, sblk*256]
+  float* tau_score;      // [nq_total]
+  uint32_t* tau_idx;     // [nq_total]
+  uint32_t* cnt;         // [nq_total] candidates appended per query (may exceed cap -> overflow)
+  unsigned long long* cand;  // [nq_total, cap]
+  int cap;
+};
+
+// first row of sample block j (strided over the whole shard so clustered / sorted databases are sampled fairly)
+__host__ __device__ __forceinline__ long long sample_block_row0(int j, int nblk, int sblk) {
+  return ((long long)j * nblk / sblk) * (long long)kSampleBlockRows;
+}
+
+#ifdef __CUDACC__
+// append one candidate; cnt is allowed to run past cap (detected by the final select)
+__device__ __forceinline__ void push_candidate(const SimParams& p, int q, float score, uint32_t idx) {
+  const uint32_t slot = atomicAdd(&p.cnt[q], 1u);
+  if (slot < (uint32_t)p.cap) p.cand[(size_t)q * p.cap + slot] = make_key(score, idx);
+}
+__device__ __forceinline__ bool passes(float score, uint32_t idx, float ts, uint32_t ti) {
+  return score > ts || (score == ts && idx <= ti);
+}
+#endif
+
+// kernels' host launchers (defined in the .cu files)
+int launch_sim_stream(const SimParams& p, int dtype, cudaStream_t st);
+int launch_sim_mma(const SimParams& p, int dtype, cudaStream_t st);
+int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st);
+int launch_final_select(const SimParams& p, int nq_total, int k, long long idx_offset, float* out_score,
+                        int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
+int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
+                      int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);
+
+}  // namespace rir

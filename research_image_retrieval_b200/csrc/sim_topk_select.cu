@@ -1,0 +1,284 @@
+// sim_topk_select.cu — the ranking side of sim_topk: sample threshold, final exact select, robust fallback scan,
+// and the cross-shard k-way merge.
+//
+// Replaces np.argsort(-similarity, axis=1) (iris_evaluate.py:386) / torch.topk(similarity, k)
+// (reference/manus/7_AdaptiveHybridModel/modified/adaptive_hybrid_retrieval_complete.py:428): the [nq, n] matrix is
+// never sorted; only the candidates that survive the per-query threshold are.
+#include "sim_topk.cuh"
+#include "topk_select.cuh"
+
+namespace rir {
+
+constexpr int kSelectThreads = 512;
+
+// ---------------------------------------------------------------------------------------------
+// tau[q] = k-th best key of the dense sample scores
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelectThreads) sample_threshold_kernel(const SimParams p, int k, int kpad) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ SelectScratch sc;
+  const int q = blockIdx.x;
+  const int m = p.sblk * kSampleBlockRows;
+  const float* s = p.sample_scores + (size_t)q * m;
+  const int nblk = p.nblk, sblk = p.sblk;
+  auto key_at = [=](int i) -> unsigned long long {
+    const long long row = sample_block_row0(i / kSampleBlockRows, nblk, sblk) + (i % kSampleBlockRows);
+    return make_key(s[i], (uint32_t)row);
+  };
+  const int got = block_select_topk(key_at, m, k, dst, kpad, &sc);
+  if (threadIdx.x == 0) {
+    // got == k whenever the host sized the sample (S >= k valid rows); otherwise fall back to "accept everything"
+    if (got >= k && key_score(dst[k - 1]) > -INFINITY) {
+      p.tau_score[q] = key_score(dst[k - 1]);
+      p.tau_idx[q] = key_index(dst[k - 1]);
+    } else {
+      p.tau_score[q] = -INFINITY;
+      p.tau_idx[q] = 0xFFFFFFFFu;
+    }
+  }
+}
+
+int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st) {
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  RIR_CUDA_OK(cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sample_threshold_kernel<<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad);
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// final: exact top-k of each query's candidate list
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_sorted(const uint64_t* dst, int got, int k, long long idx_offset,
+                                             float* out_score, int32_t* out_idx) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const uint64_t key = dst[i];
+    if (i < got && key != 0ull) {
+      out_score[i] = key_score(key);
+      out_idx[i] = (int32_t)((long long)key_index(key) + idx_offset);
+    } else {
+      out_score[i] = -INFINITY;
+      out_idx[i] = -1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+    final_select_kernel(const SimParams p, int k, int kpad, long long idx_offset, float* out_score, int32_t* out_idx,
+                        uint32_t* ovf) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ SelectScratch sc;
+  const int q = blockIdx.x;
+  const uint32_t cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : p.cnt[q];  // scan-all: slot == row
+  if (cnt > (uint32_t)p.cap) {  // candidate list overflowed: the exact fallback kernel owns this query
+    if (threadIdx.x == 0) ovf[q] = 1u;
+    return;
+  }
+  if (threadIdx.x == 0) ovf[q] = 0u;
+  const unsigned long long* c = p.cand + (size_t)q * p.cap;
+  auto key_at = [=](int i) -> unsigned long long { return c[i]; };
+  const int got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+}
+
+int launch_final_select(const SimParams& p, int nq_total, int k, long long idx_offset, float* out_score,
+                        int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  final_select_kernel<<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// robust exact scan: one CTA per query, running top-k in shared memory.  Used (a) for queries whose candidate
+// list overflowed, (b) as RIR_PATH_EXACT — an independent second implementation for the parity tests.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExactThreads = 256;
+constexpr int kExactRowsPerIter = 32;  // 8 warps x 4 rows
+
+template <int DT>
+__device__ __forceinline__ float dot_row(const uint8_t* row, const float* qs, int chunks, int lane);
+
+template <>
+__device__ __forceinline__ float dot_row<RIR_BF16>(const uint8_t* row, const float* qs, int chunks, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
+    const float4 q0 = reinterpret_cast<const float4*>(qs)[2 * c], q1 = reinterpret_cast<const float4*>(qs)[2 * c + 1];
+    acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
+    acc = fmaf(__uint_as_float(v.x & 0xffff0000u), q0.y, acc);
+    acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
+    acc = fmaf(__uint_as_float(v.y & 0xffff0000u), q0.w, acc);
+    acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
+    acc = fmaf(__uint_as_float(v.z & 0xffff0000u), q1.y, acc);
+    acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
+    acc = fmaf(__uint_as_float(v.w & 0xffff0000u), q1.w, acc);
+  }
+  return warp_sum(acc);
+}
+template <>
+__device__ __forceinline__ float dot_row<RIR_F32>(const uint8_t* row, const float* qs, int chunks, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
+    const float4 q0 = reinterpret_cast<const float4*>(qs)[c];
+    acc = fmaf(__uint_as_float(v.x), q0.x, acc);
+    acc = fmaf(__uint_as_float(v.y), q0.y, acc);
+    acc = fmaf(__uint_as_float(v.z), q0.z, acc);
+    acc = fmaf(__uint_as_float(v.w), q0.w, acc);
+  }
+  return warp_sum(acc);
+}
+__device__ __forceinline__ void fp8x4_to_float(uint32_t w, float* f) {
+  const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xffffu), __NV_E4M3);
+  const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w >> 16), __NV_E4M3);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+template <>
+__device__ __forceinline__ float dot_row<RIR_FP8E4M3>(const uint8_t* row, const float* qs, int chunks, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
+    const float* qp = qs + (size_t)c * 16;
+    float f[16];
+    fp8x4_to_float(v.x, f); fp8x4_to_float(v.y, f + 4); fp8x4_to_float(v.z, f + 8); fp8x4_to_float(v.w, f + 12);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc = fmaf(f[e], qp[e], acc);
+  }
+  return warp_sum(acc);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kExactThreads)
+    exact_scan_kernel(const SimParams p, int k, int bufcap, long long idx_offset, float* out_score, int32_t* out_idx,
+                      const uint32_t* ovf) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int q = blockIdx.x;
+  if (ovf != nullptr && ovf[q] == 0u) return;
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);           // [bufcap]
+  float* qs = reinterpret_cast<float*>(buf + bufcap);              // [d]
+  __shared__ int count;
+  __shared__ unsigned long long tau;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) {
+    float v;
+    if (DT == RIR_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.Q)[(size_t)q * p.d + i]);
+    else if (DT == RIR_F32) v = reinterpret_cast<const float*>(p.Q)[(size_t)q * p.d + i];
+    else {
+      const __half_raw h =
+          __nv_cvt_fp8_to_halfraw(reinterpret_cast<const __nv_fp8_storage_t*>(p.Q)[(size_t)q * p.d + i], __NV_E4M3);
+      v = __half2float(*reinterpret_cast<const __half*>(&h));
+    }
+    if (p.q_scale) v *= p.q_scale[q];
+    qs[i] = v;
+  }
+  for (int i = threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
+  if (threadIdx.x == 0) { count = 0; tau = 0ull; }
+  __syncthreads();
+  const int chunks = p.row_bytes >> 4;
+  for (long long base = 0; base < p.n; base += kExactRowsPerIter) {
+    const unsigned long long t = tau;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long row = base + warp * 4 + r;
+      if (row < p.n) {
+        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
+        if (p.x_scale) s *= p.x_scale[row];
+        const unsigned long long key = make_key(s, (uint32_t)row);
+        if (lane == 0 && key > t) buf[atomicAdd(&count, 1)] = key;
+      }
+    }
+    __syncthreads();
+    if (count > bufcap - kExactRowsPerIter) {  // uniform branch: compact to the best k
+      block_bitonic_sort_desc(buf, bufcap);
+      if (threadIdx.x == 0 && count >= k) {
+        count = k;
+        tau = buf[k - 1];
+      }
+      for (int i = k + threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
+    }
+    __syncthreads();
+  }
+  block_bitonic_sort_desc(buf, bufcap);
+  const int got = count < k ? count : k;
+  write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+}
+
+int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
+                      int32_t* out_idx, const uint32_t* ovf, cudaStream_t st) {
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  // room for k survivors + one iteration of pushes; all rows fit when n <= kpad (full ranking)
+  int bufcap = (p.n <= (long long)kpad) ? kpad : 2 * kpad;
+  if (bufcap < 64) bufcap = 64;
+  const size_t smem = (size_t)bufcap * sizeof(uint64_t) + (size_t)p.d * sizeof(float);
+  if (smem > 220 * 1024) {
+    set_error("sim_topk(exact): k=%d with n=%lld needs %zu B of shared memory", k, p.n, smem);
+    return RIR_E_ARG;
+  }
+  if (dtype == RIR_BF16) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exact_scan_kernel<RIR_BF16><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
+  } else if (dtype == RIR_FP8E4M3) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exact_scan_kernel<RIR_FP8E4M3><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
+  } else if (dtype == RIR_F32) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exact_scan_kernel<RIR_F32><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
+  } else {
+    set_error("sim_topk(exact): unsupported dtype %d", dtype);
+    return RIR_E_ARG;
+  }
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-shard merge: [G, nq, k] sorted lists -> global top-k
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelectThreads)
+    merge_topk_kernel(const float* sc, const int32_t* ix, int G, int nq, int k, int kpad, float* out_sc,
+                      int32_t* out_ix) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ SelectScratch scr;
+  const int q = blockIdx.x;
+  auto key_at = [=](int i) -> unsigned long long {
+    const int g = i / k, j = i - g * k;
+    const size_t o = ((size_t)g * nq + q) * k + j;
+    const int32_t id = ix[o];
+    return id < 0 ? 0ull : make_key(sc[o], (uint32_t)id);
+  };
+  const int got = block_select_topk(key_at, G * k, k, dst, kpad, &scr);
+  write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+}
+
+}  // namespace rir
+
+extern "C" size_t rir_merge_topk_workspace(int G, int nq, int k) {
+  (void)G; (void)nq; (void)k;
+  return 0;  // the merge runs entirely in shared memory
+}
+
+extern "C" int rir_merge_topk(const float* sc, const int32_t* ix, int G, int nq, int k, float* out_sc, int32_t* out_ix,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  using namespace rir;
+  if (int e = check_arch()) return e;
+  RIR_REQUIRE(sc && ix && out_sc && out_ix, "merge_topk: null pointer");
+  RIR_REQUIRE(G >= 1 && nq >= 0 && k >= 1 && k <= 16384, "merge_topk: bad shape G=%d nq=%d k=%d", G, nq, k);
+  RIR_REQUIRE((long long)G * k < (1ll << 30), "merge_topk: G*k too large");
+  if (nq == 0) return RIR_OK;
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  RIR_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<nq, kSelectThreads, smem, (cudaStream_t)stream>>>(sc, ix, G, nq, k, kpad, out_sc, out_ix);
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}

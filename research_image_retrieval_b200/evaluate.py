@@ -1,0 +1,200 @@
+"""Revisited-protocol evaluation on the GPU — drop-in for the reference's `utils/evaluate.py`.
+
+Same call signatures, return arity, printed text, `inf` conventions, exceptions and 2-dp rounding as
+
+  compute_ap            utils/evaluate.py:4-34
+  compute_map           utils/evaluate.py:37-150
+  compute_map_and_print utils/evaluate.py:153-194          (duplicate copies at iris_evaluate.py:11-265)
+
+The arithmetic runs in `rir_compute_map` (csrc/evaluate_map.cu) in fp64 with the reference's operation order, so the
+returned numbers equal the reference's Python floats.  Host code here only converts the ground-truth dictionaries to
+sorted CSR id lists and formats the results.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PROTO_OK_A_JUNK_C = 0x41       # compute_map: ok = list A, junk = list C
+PROTO_EASY = 0x61              # ok = easy(A)        junk = junk(C) | hard(B)     utils/evaluate.py:163-169
+PROTO_MEDIUM = 0x43            # ok = easy | hard    junk = junk                  utils/evaluate.py:171-177
+PROTO_HARD = 0x52              # ok = hard(B)        junk = junk(C) | easy(A)     utils/evaluate.py:179-185
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side format conversion (no arithmetic)
+# ----------------------------------------------------------------------------------------------
+def ids_to_csr(lists):
+    """[array-like of ids per query] -> (ids int32 sorted within each query, off int32[nq+1]).
+
+    Duplicates are kept: the reference uses len(ok) (duplicates included) as the number of positives."""
+    off = np.zeros(len(lists) + 1, dtype=np.int32)
+    parts = []
+    for i, l in enumerate(lists):
+        a = np.asarray(l).reshape(-1)
+        if a.size and not np.issubdtype(a.dtype, np.integer):
+            a = a.astype(np.int64)
+        a = np.sort(a.astype(np.int32, copy=False)) if a.size else np.empty(0, dtype=np.int32)
+        parts.append(a)
+        off[i + 1] = off[i] + a.size
+    ids = np.concatenate(parts) if parts else np.empty(0, dtype=np.int32)
+    return np.ascontiguousarray(ids, dtype=np.int32), off
+
+
+def ranks_to_rows(ranks, li: bool, nq: int):
+    """Reference layouts -> row-per-query int32 [nq, L] on the host or device; -1 pads ragged lists.
+
+    li=False: `ranks` is [L, nq] (column per query, utils/evaluate.py:49,79); li=True: list of nq ranked lists."""
+    if li:
+        lens = [len(r) for r in ranks]
+        L = max(lens) if lens else 0
+        rows = np.full((nq, max(L, 1)), -1, dtype=np.int32)
+        for i in range(nq):
+            if lens[i]:
+                rows[i, : lens[i]] = np.asarray(ranks[i], dtype=np.int64)
+        return rows, L
+    if isinstance(ranks, torch.Tensor):
+        if ranks.dim() != 2:
+            raise ValueError("ranks must be 2-D [L, nq]")
+        return ranks.t().to(torch.int32).contiguous(), ranks.shape[0]
+    r = np.asarray(ranks)
+    if r.ndim != 2:
+        raise ValueError("ranks must be 2-D [L, nq]")
+    return np.ascontiguousarray(r.T.astype(np.int32)), r.shape[0]
+
+
+def _dev(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def _run_map(rows, L, nq, lists_abc, protos, keeps, device=None):
+    """Launch rir_compute_map; returns host numpy (map[P], aps[P,nq], mpr[P,nk], prs[P,nq,nk], status[P,nq])."""
+    lib = _lib.load()
+    if device is None:
+        device = rows.device if isinstance(rows, torch.Tensor) and rows.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    rows_d = _dev(rows, device)
+    ld = rows_d.shape[1]
+    ptrs = []
+    keepalive = []
+    for lst in lists_abc:
+        if lst is None:
+            ptrs += [None, None]
+            continue
+        ids, off = lst
+        ids_d = _dev(ids if ids.size else np.zeros(1, dtype=np.int32), device)
+        off_d = _dev(off, device)
+        keepalive += [ids_d, off_d]
+        ptrs += [ids_d.data_ptr(), off_d.data_ptr()]
+    P = len(protos)
+    keeps = list(keeps) if keeps else []
+    nk = len(keeps)
+    out_map = torch.empty(P, dtype=torch.float64, device=device)
+    out_aps = torch.empty((P, nq), dtype=torch.float64, device=device)
+    out_mpr = torch.empty((P, max(nk, 1)), dtype=torch.float64, device=device)
+    out_prs = torch.empty((P, nq, max(nk, 1)), dtype=torch.float64, device=device)
+    out_status = torch.empty((P, nq), dtype=torch.int32, device=device)
+    proto_arr = (ctypes.c_int32 * P)(*protos)
+    kappa_arr = (ctypes.c_int32 * max(nk, 1))(*([int(k) for k in keeps] or [0]))
+    with torch.cuda.device(device):
+        _lib.check(lib.rir_compute_map(rows_d.data_ptr(), nq, int(L), int(ld), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                       ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk, out_map.data_ptr(),
+                                       out_aps.data_ptr(), out_mpr.data_ptr(), out_prs.data_ptr(),
+                                       out_status.data_ptr(), _lib.stream_ptr()))
+    res = (out_map.cpu().numpy(), out_aps.cpu().numpy(), out_mpr.cpu().numpy()[:, :nk],
+           out_prs.cpu().numpy()[:, :, :nk], out_status.cpu().numpy())
+    del keepalive
+    return res
+
+
+def _finish(map_p, aps_p, mpr_p, prs_p, status_p, keeps):
+    """Apply the reference's Python-level conventions to one protocol's raw outputs."""
+    nq = aps_p.shape[0]
+    if keeps and np.any(status_p == _lib.RIR_MAP_NO_POS_RETRIEVED):
+        # utils/evaluate.py:101 — max(pos) over an empty array
+        raise ValueError("max() iterable argument is empty")
+    if np.all(status_p == _lib.RIR_MAP_EMPTY_OK):
+        # utils/evaluate.py:105 — Python float divided by the int 0
+        raise ZeroDivisionError("float division by zero")
+    if keeps:
+        return np.float64(map_p), aps_p.copy(), mpr_p.copy(), prs_p.reshape(nq, len(keeps)).copy()
+    return np.float64(map_p), aps_p.copy()
+
+
+# ----------------------------------------------------------------------------------------------
+# reference API
+# ----------------------------------------------------------------------------------------------
+def compute_ap(ranks, nres):
+    """Average precision from the zero-based, junk-adjusted ranks of the positives (utils/evaluate.py:4-34).
+
+    Evaluated by the same GPU kernel as compute_map: the ranks become a ranked list with the positive id 1 at the
+    given positions and `nres` copies of id 1 as the ok list (len(ok) == nres)."""
+    r = np.asarray(ranks, dtype=np.int64).reshape(-1)
+    if r.size == 0:
+        return 0.0
+    if np.any(np.diff(r) <= 0) or r[0] < 0:
+        raise ValueError("compute_ap expects strictly increasing zero-based ranks")
+    L = int(r[-1]) + 1
+    rows = np.zeros((1, L), dtype=np.int32)
+    rows[0, r] = 1
+    ok = (np.ones(int(nres), dtype=np.int32), np.array([0, int(nres)], dtype=np.int32))
+    m, aps, _, _, _ = _run_map(rows, L, 1, [ok, None, None], [PROTO_OK_A_JUNK_C], None)
+    return float(aps[0, 0])
+
+
+def compute_map(ranks, gnd, keeps=None, li=False):
+    """mAP (and mP@k) of ranked lists against {'ok', 'junk'} ground truth — utils/evaluate.py:37-150.
+
+    ranks: int array [L, nq] (column per query; L may be a truncated top-k) or, with li=True, a list of nq ranked lists
+    of possibly different lengths.  Returns (mAP, aps) or, with `keeps`, (mAP, aps, pr, prs)."""
+    nq = len(gnd)
+    ok = ids_to_csr([g["ok"] for g in gnd])
+    junk_lists = []
+    for g in gnd:
+        try:
+            junk_lists.append(g["junk"])
+        except Exception:  # the reference tolerates a missing 'junk' key (utils/evaluate.py:70-73)
+            junk_lists.append([])
+    junk = ids_to_csr(junk_lists)
+    rows, L = ranks_to_rows(ranks, li, nq)
+    m, aps, mpr, prs, status = _run_map(rows, L, nq, [ok, None, junk], [PROTO_OK_A_JUNK_C], keeps)
+    return _finish(m[0], aps[0], mpr[0], prs[0], status[0], keeps)
+
+
+def revisited_map(ranks, gnd, kappas=(1, 5, 10), li=False):
+    """Easy / Medium / Hard in ONE launch.  Returns [(mAP, aps, mpr, prs)] * 3 (E, M, H)."""
+    nq = len(gnd)
+    easy = ids_to_csr([g["easy"] for g in gnd])
+    hard = ids_to_csr([g["hard"] for g in gnd])
+    junk = ids_to_csr([g["junk"] for g in gnd])
+    rows, L = ranks_to_rows(ranks, li, nq)
+    kappas = list(kappas)
+    m, aps, mpr, prs, status = _run_map(rows, L, nq, [easy, hard, junk], [PROTO_EASY, PROTO_MEDIUM, PROTO_HARD], kappas)
+    return [_finish(m[p], aps[p], mpr[p], prs[p], status[p], kappas) for p in range(3)]
+
+
+def compute_map_and_print(dataset, featuretype, mode, ranks, gnd, kappas=[1, 5, 10], verbose=False, li=False):
+    """utils/evaluate.py:153-194 — same prints, same 2-dp rounded (mapE, mapM, mapH) return."""
+    # old evaluation protocol: the reference unpacks 4 values from a 2-tuple and raises (utils/evaluate.py:157)
+    if dataset.startswith('oxford5k') or dataset.startswith('paris6k'):
+        map, aps, _, _ = compute_map(ranks, gnd)
+        print('>> {}: mAP {:.2f}'.format(dataset, np.around(map * 100, decimals=2)))
+
+    # new evaluation protocol
+    elif dataset.startswith('roxford5k') or dataset.startswith('rparis6k'):
+        (mapE, apsE, mprE, prsE), (mapM, apsM, mprM, prsM), (mapH, apsH, mprH, prsH) = \
+            revisited_map(ranks, gnd, kappas, li=li)
+
+        print('>> Test Dataset: {} *** Feature Type: {} >>'.format(dataset, featuretype))
+        print('>> mAP Eeay: {}, Medium: {}, Hard: {}'.format(np.around(mapE * 100, decimals=2), np.around(mapM * 100, decimals=2), np.around(mapH * 100, decimals=2)))
+        print('>> mP@k{} Easy: {}, Medium: {}, Hard: {}'.format(kappas, np.around(mprE * 100, decimals=2), np.around(mprM * 100, decimals=2), np.around(mprH * 100, decimals=2)))
+
+        if verbose:
+            print('>> Query aps: >>\nEeay: {}\nMedium: {}\nHard: {}'.format(np.around(apsE * 100, decimals=2), np.around(apsM * 100, decimals=2), np.around(apsH * 100, decimals=2)))
+
+        return np.around(mapE * 100, decimals=2), np.around(mapM * 100, decimals=2), np.around(mapH * 100, decimals=2)

@@ -1,0 +1,190 @@
+"""Descriptor heads: pooling -> L2 -> whitening -> L2, on librir.so kernels.
+
+Drop-in mirrors (same names, constructor arguments and output shapes) of the reference's inference-time heads:
+
+  gem, spoc            networks/RetrievalNet.py:318-325, 359-365
+  GeMPooling           models/gem_pooling.py:12-23          (learnable tensor p)
+  G2Pooling            models/senet_g2.py:132-153           (alpha * gem + beta)
+  mac / MACPooling     models/spoc.py:12-49 level 1 max
+  l2n                  F.normalize(x, p=2, dim=-1)          (networks/RetrievalNet.py:343 ...)
+  whiten               1x1 conv / Linear W x + b            (networks/RetrievalNet.py:342,588; networks/spca.py:61-64)
+  DescriptorHead       GeM.forward_test / SOLAR.forward_test tail (networks/RetrievalNet.py:337-344, 583-590)
+
+These are inference (`forward_test`) paths: the kernels do not record autograd graphs.  Inputs must be CUDA tensors on
+a B200; there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RIR_BF16, RIR_F32, RIR_POOL_AVG, RIR_POOL_GEM, RIR_POOL_MAX
+
+
+def _pool(x: torch.Tensor, mode: int, p: float = 3.0, eps: float = 1e-6, alpha: float = 1.0, beta: float = 0.0,
+          keepdim: bool = True) -> torch.Tensor:
+    if x.dim() != 4:
+        raise ValueError(f"expected a [B, C, H, W] feature map, got shape {tuple(x.shape)}")
+    if x.dtype == torch.float32:
+        dt = RIR_F32
+    elif x.dtype == torch.bfloat16:
+        dt = RIR_BF16
+    else:
+        raise TypeError(f"feature maps must be float32 or bfloat16, got {x.dtype}")
+    if not x.is_cuda:
+        raise TypeError("feature maps must be CUDA tensors (no CPU path)")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rir_pool(x.data_ptr(), dt, B, C, H * W, mode, float(p), float(eps), float(alpha),
+                                        float(beta), out.data_ptr(), _lib.stream_ptr()))
+    return out.view(B, C, 1, 1) if keepdim else out
+
+
+def gem_pool(x, p=3.0, eps=1e-6, keepdim=True):
+    """(mean_hw clamp(x, eps)^p)^(1/p) — F.avg_pool2d(x.clamp(min=eps).pow(p), (H, W)).pow(1/p)."""
+    return _pool(x, RIR_POOL_GEM, p=float(p), eps=eps, keepdim=keepdim)
+
+
+def mac_pool(x, keepdim=True):
+    """Global max over H x W (MAC; SpatialPyramidPooling level 1, pool_type='max')."""
+    return _pool(x, RIR_POOL_MAX, keepdim=keepdim)
+
+
+def spoc_pool(x, eps=1e-6, keepdim=True):
+    """F.avg_pool2d(x.clamp(min=eps), (H, W))."""
+    return _pool(x, RIR_POOL_AVG, eps=eps, keepdim=keepdim)
+
+
+def l2n(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=-1) for a [..., D] fp32 CUDA tensor."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("l2n expects a float32 CUDA tensor")
+    x = x.contiguous()
+    d = x.shape[-1]
+    n = x.numel() // d if d else 0
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rir_l2_normalize(x.data_ptr(), n, d, float(eps), out.data_ptr(), _lib.stream_ptr()))
+    return out
+
+
+def whiten(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, l2_after: bool = False):
+    """y = W x + b for pooled descriptors.
+
+    x: [B, C] or [B, C, 1, 1];  weight: [d_out, C] (Linear) or [d_out, C, 1, 1] (1x1 Conv2d);  returns [B, d_out].
+    """
+    x2 = x.reshape(x.shape[0], -1).contiguous().float()
+    w2 = weight.reshape(weight.shape[0], -1).contiguous().float()
+    if not (x2.is_cuda and w2.is_cuda):
+        raise TypeError("whiten expects CUDA tensors")
+    if x2.shape[1] != w2.shape[1]:
+        raise ValueError(f"whiten: x has {x2.shape[1]} channels, weight expects {w2.shape[1]}")
+    b = None if bias is None else bias.contiguous().float()
+    out = torch.empty((x2.shape[0], w2.shape[0]), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(_lib.load().rir_whiten(x2.data_ptr(), w2.data_ptr(), None if b is None else b.data_ptr(),
+                                          x2.shape[0], x2.shape[1], w2.shape[0], 1 if l2_after else 0, out.data_ptr(),
+                                          _lib.stream_ptr()))
+    return out
+
+
+class gem(nn.Module):
+    """networks/RetrievalNet.py:318-325 — fixed p, returns [B, C, 1, 1]."""
+
+    def __init__(self, p=3.0, eps=1e-6):
+        super().__init__()
+        self.p = p
+        self.eps = eps
+
+    def forward(self, x):
+        return gem_pool(x, self.p, self.eps)
+
+
+class spoc(nn.Module):
+    """networks/RetrievalNet.py:359-365."""
+
+    def __init__(self, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x):
+        return spoc_pool(x, self.eps)
+
+
+class GeMPooling(nn.Module):
+    """models/gem_pooling.py:12-23 — p is an nn.Parameter of shape [1]."""
+
+    def __init__(self, p=3.0, eps=1e-6):
+        super().__init__()
+        self.p = nn.Parameter(torch.ones(1) * p)
+        self.eps = eps
+
+    def forward(self, x):
+        return gem_pool(x, float(self.p.detach().reshape(-1)[0]), self.eps)
+
+
+class G2Pooling(nn.Module):
+    """models/senet_g2.py:132-153 — alpha * GeM(x) + beta."""
+
+    def __init__(self, p=3.0, eps=1e-6):
+        super().__init__()
+        self.p = nn.Parameter(torch.ones(1) * p)
+        self.eps = eps
+        self.alpha = nn.Parameter(torch.ones(1))
+        self.beta = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        return _pool(x, RIR_POOL_GEM, p=float(self.p.detach()[0]), eps=self.eps, alpha=float(self.alpha.detach()[0]),
+                     beta=float(self.beta.detach()[0]))
+
+
+class MACPooling(nn.Module):
+    """Global max pooling — SpatialPyramidPooling(levels=[1], pool_type='max') (models/spoc.py:12-49)."""
+
+    def forward(self, x):
+        return mac_pool(x)
+
+
+def ultron_gem_pooling(x, gamma):
+    """AttentionBasedGlobalPooling.gem_pooling (models/ultron_modules/ultron.py:193-205): p clamped to [1e-7, 100],
+    eps 1e-7, returns [B, C]."""
+    g = float(torch.as_tensor(gamma).detach().reshape(-1)[0])
+    g = min(max(g, 1e-7), 100.0)
+    return _pool(x, RIR_POOL_GEM, p=g, eps=1e-7, keepdim=False)
+
+
+class DescriptorHead(nn.Module):
+    """pool -> [L2] -> whiten (+bias) -> L2, the tail of GeM.forward_test (networks/RetrievalNet.py:337-344,
+    l2_before_whiten=False) and SOLAR.forward_test (networks/RetrievalNet.py:583-590, l2_before_whiten=True).
+
+    `whiten_layer` may be the reference's nn.Conv2d(1x1) / nn.Linear / ConvDimReduction, or None (pool + L2 only,
+    e.g. models/gem_pooling.py:86-92).
+    """
+
+    def __init__(self, pooling: str = "gem", p: float = 3.0, eps: float = 1e-6, whiten_layer: nn.Module | None = None,
+                 l2_before_whiten: bool = False):
+        super().__init__()
+        if pooling not in ("gem", "mac", "spoc"):
+            raise ValueError(f"unknown pooling {pooling!r}")
+        self.pooling = pooling
+        self.p = p
+        self.eps = eps
+        self.whiten_layer = whiten_layer
+        self.l2_before_whiten = l2_before_whiten
+
+    @torch.no_grad()
+    def forward(self, feature_map: torch.Tensor) -> torch.Tensor:
+        if self.pooling == "gem":
+            v = gem_pool(feature_map, self.p, self.eps, keepdim=False)
+        elif self.pooling == "mac":
+            v = mac_pool(feature_map, keepdim=False)
+        else:
+            v = spoc_pool(feature_map, self.eps, keepdim=False)
+        if self.whiten_layer is None:
+            return l2n(v)
+        if self.l2_before_whiten:
+            v = l2n(v)
+        return whiten(v, self.whiten_layer.weight, self.whiten_layer.bias, l2_after=True)

@@ -1,0 +1,328 @@
+"""Similarity search: exact Q·Xᵀ top-k, sharded merge and alpha query expansion on librir.so kernels.
+
+Drop-in for the reference's similarity + ranking call site
+
+    similarity = torch.mm(query_features, gallery_features.t()).cpu().numpy()      iris_evaluate.py:383
+    ranks = np.argsort(-similarity, axis=1)                                         iris_evaluate.py:386
+
+and its top-k precedent `compute_similarity` + `torch.topk(similarity, k)`
+(reference/manus/7_AdaptiveHybridModel/modified/adaptive_hybrid_retrieval_complete.py:11-16, 428).
+
+  rank(q, g, k=None)        -> int64 ndarray [k_or_N, nq]   (column per query — the layout compute_map documents,
+                                                             utils/evaluate.py:49)
+  Database / sim_topk       -> resident bf16 / fp8 / fp32 descriptor shard + exact top-k
+  ShardedDatabase           -> row-sharded over the ranks of a torch.distributed group, allgather + merge_topk
+  alpha_query_expansion     -> q' = L2(q + sum_j max(s_j,0)^alpha x_j), then search again
+
+Order rule everywhere: descending score, ties -> ascending database index.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PATHS, RIR_BF16, RIR_F32, RIR_FP8E4M3
+
+_DTYPES = {"bf16": RIR_BF16, "fp8": RIR_FP8E4M3, "fp32": RIR_F32}
+_TORCH_DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
+if hasattr(torch, "float8_e4m3fn"):
+    _TORCH_DT["fp8"] = torch.float8_e4m3fn
+
+MAX_K_FILTER = 8192          # k limit for shards larger than MAX_FULL_RANK rows (include/rir.h)
+MAX_FULL_RANK = 16384        # shards up to this many rows can be ranked completely
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side helpers (pure logic; unit-tested on CPU)
+# ----------------------------------------------------------------------------------------------
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Row range [lo, hi) of shard `rank`: ceil(n / world) rows each, the last one shorter."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad shard {rank}/{world}")
+    per = -(-n // world)
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def pad_dim(d: int, dtype: str) -> int:
+    """Descriptor rows must be a multiple of 16 bytes (TMA / 128-bit loads); zero padding leaves dot products unchanged."""
+    esz = {"bf16": 2, "fp8": 1, "fp32": 4}[dtype]
+    per = 16 // esz
+    return -(-d // per) * per
+
+
+def clamp_k(k: Optional[int], n: int) -> int:
+    if k is None:
+        k = n
+    k = int(k)
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    return min(k, n)
+
+
+def check_k_supported(k: int, n_local: int) -> None:
+    if n_local > MAX_FULL_RANK and k > MAX_K_FILTER:
+        raise ValueError(f"k={k} is not supported for a shard of {n_local} rows: k <= {MAX_K_FILTER}, "
+                         f"or a full ranking for shards of at most {MAX_FULL_RANK} rows")
+
+
+def merge_topk_host(scores: np.ndarray, idx: np.ndarray, k: int):
+    """Reference semantics of the cross-shard merge on [G, nq, k] arrays (numpy; used by the CPU tests of the
+    multi-rank plumbing — the product path is rir_merge_topk)."""
+    G, nq, kk = scores.shape
+    s = np.transpose(scores, (1, 0, 2)).reshape(nq, G * kk)
+    i = np.transpose(idx, (1, 0, 2)).reshape(nq, G * kk)
+    s = np.where(i < 0, -np.inf, s)
+    big = np.iinfo(np.int64).max
+    order = np.lexsort((np.where(i < 0, big, i.astype(np.int64)), -s.astype(np.float64)), axis=1)[:, :k]
+    return np.take_along_axis(s, order, 1), np.take_along_axis(i, order, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# packed descriptor shards
+# ----------------------------------------------------------------------------------------------
+def pack_descriptors(v: torch.Tensor, dtype: str = "bf16"):
+    """fp32 [n, d] CUDA descriptors -> (rows in the search dtype [n, d_pad], per-row scale or None)."""
+    if dtype not in _DTYPES:
+        raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+    if not v.is_cuda:
+        raise TypeError("descriptors must be on the GPU (no CPU path)")
+    v = v.float().contiguous()
+    n, d = v.shape
+    dp = pad_dim(d, dtype)
+    if dp != d:
+        v = torch.nn.functional.pad(v, (0, dp - d))
+    if dtype == "fp32":
+        return v, None
+    lib = _lib.load()
+    if dtype == "bf16":
+        out = torch.empty((n, dp), dtype=torch.bfloat16, device=v.device)
+        scale = None
+    else:
+        out = torch.empty((n, dp), dtype=torch.uint8, device=v.device)
+        scale = torch.empty(n, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(lib.rir_pack_descriptors(v.data_ptr(), n, dp, _DTYPES[dtype], out.data_ptr(),
+                                            None if scale is None else scale.data_ptr(), _lib.stream_ptr()))
+    return out, scale
+
+
+class Database:
+    """One resident shard of database descriptors in the layout the search kernels read.
+
+    rows: [n_local, d] bf16 / uint8(fp8 e4m3) / fp32, row-major, 16-byte-multiple rows; scale: per-row fp32 or None;
+    idx_offset: global index of local row 0."""
+
+    def __init__(self, rows: torch.Tensor, scale: Optional[torch.Tensor], dtype: str, idx_offset: int = 0,
+                 d_logical: Optional[int] = None):
+        self.rows, self.scale, self.dtype, self.idx_offset = rows, scale, dtype, int(idx_offset)
+        self.n, self.d = rows.shape
+        self.d_logical = d_logical or self.d
+        self._ws = None
+
+    @classmethod
+    def from_descriptors(cls, v: torch.Tensor, dtype: str = "bf16", idx_offset: int = 0, normalize: bool = False):
+        if normalize:
+            from .pooling import l2n
+            v = l2n(v.float().contiguous())
+        rows, scale = pack_descriptors(v, dtype)
+        return cls(rows, scale, dtype, idx_offset, d_logical=v.shape[1])
+
+    def pack_queries(self, q: torch.Tensor):
+        """fp32 [nq, d_logical] -> the shard's dtype (padded like the rows)."""
+        if q.shape[1] != self.d_logical:
+            raise ValueError(f"query dimension {q.shape[1]} != database dimension {self.d_logical}")
+        return pack_descriptors(q.to(self.rows.device), self.dtype)
+
+    def workspace(self, nq: int, k: int) -> torch.Tensor:
+        need = _lib.load().rir_sim_topk_workspace(nq, self.n, self.d, k, _DTYPES[self.dtype])
+        if need == 0 and not (nq == 0):
+            raise ValueError(f"unsupported search shape nq={nq} n={self.n} d={self.d} k={k}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.rows.device)
+        return self._ws
+
+    def search(self, q_rows: torch.Tensor, q_scale: Optional[torch.Tensor], k: int, path: str = "auto"):
+        """Exact local top-k.  Returns (scores [nq, k] fp32, idx [nq, k] int32 GLOBAL indices) on the GPU."""
+        return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
+                        idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k))
+
+
+def sim_topk(Q: torch.Tensor, X: torch.Tensor, k: int, dtype: str = "bf16", q_scale=None, x_scale=None,
+             idx_offset: int = 0, path: str = "auto", workspace: Optional[torch.Tensor] = None, out=None):
+    """Thin wrapper over rir_sim_topk (include/rir.h).  Q [nq, d], X [n, d] already in the search dtype."""
+    lib = _lib.load()
+    if dtype not in _DTYPES:
+        raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+    if path not in PATHS:
+        raise ValueError(f"path must be one of {sorted(PATHS)}")
+    if not (Q.is_cuda and X.is_cuda):
+        raise TypeError("Q and X must be CUDA tensors (no CPU path)")
+    if Q.dim() != 2 or X.dim() != 2 or Q.shape[1] != X.shape[1]:
+        raise ValueError(f"shape mismatch: Q {tuple(Q.shape)} X {tuple(X.shape)}")
+    if not (Q.is_contiguous() and X.is_contiguous()):
+        raise ValueError("Q and X must be contiguous row-major")
+    nq, d = Q.shape
+    n = X.shape[0]
+    if not (1 <= k <= n):
+        raise ValueError(f"k={k} must be in [1, n={n}]")
+    check_k_supported(k, n)
+    if out is None:
+        sc = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+        ix = torch.empty((nq, k), dtype=torch.int32, device=X.device)
+    else:
+        sc, ix = out
+    if workspace is None and path != "exact":
+        need = lib.rir_sim_topk_workspace(nq, n, d, k, _DTYPES[dtype])
+        workspace = torch.empty(max(need, 256), dtype=torch.uint8, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(lib.rir_sim_topk(Q.data_ptr(), X.data_ptr(), _DTYPES[dtype],
+                                    None if q_scale is None else q_scale.data_ptr(),
+                                    None if x_scale is None else x_scale.data_ptr(), nq, n, d, k, int(idx_offset),
+                                    sc.data_ptr(), ix.data_ptr(),
+                                    None if workspace is None else workspace.data_ptr(),
+                                    0 if workspace is None else workspace.numel(), PATHS[path], _lib.stream_ptr()))
+    return sc, ix
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, k: Optional[int] = None):
+    """[G, nq, k] per-shard results -> global (scores [nq, k], idx [nq, k]) via rir_merge_topk."""
+    G, nq, kk = scores.shape
+    k = kk if k is None else k
+    if k != kk:
+        raise ValueError("merge_topk keeps k == the per-shard k")
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.load().rir_merge_topk(scores.data_ptr(), idx.data_ptr(), G, nq, k, out_s.data_ptr(),
+                                              out_i.data_ptr(), None, 0, _lib.stream_ptr()))
+    return out_s, out_i
+
+
+# ----------------------------------------------------------------------------------------------
+# reference call-site drop-in
+# ----------------------------------------------------------------------------------------------
+def rank(query_features, gallery_features, k: Optional[int] = None, dtype: str = "fp32", normalize: bool = False,
+         return_scores: bool = False, path: str = "auto", device=None):
+    """`np.argsort(-torch.mm(q, g.t()), axis=1)` without the score matrix (iris_evaluate.py:383-386).
+
+    Returns an int64 ndarray [k_or_N, nq] — column per query, the layout compute_map consumes
+    (utils/evaluate.py:49).  dtype='fp32' keeps the reference arithmetic type; 'bf16'/'fp8' use the tensor-core path.
+    normalize=True applies F.normalize to both sides first (iris_evaluate.py:379-380)."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    q = torch.as_tensor(query_features).to(device=device, dtype=torch.float32)
+    g = torch.as_tensor(gallery_features).to(device=device, dtype=torch.float32)
+    if normalize:
+        from .pooling import l2n
+        q, g = l2n(q.contiguous()), l2n(g.contiguous())
+    db = Database.from_descriptors(g, dtype)
+    k = clamp_k(k, db.n)
+    qr, qs = db.pack_queries(q)
+    sc, ix = db.search(qr, qs, k, path=path)
+    ranks = ix.t().contiguous().to(torch.int64).cpu().numpy()
+    if return_scores:
+        return ranks, sc.t().contiguous().cpu().numpy()
+    return ranks
+
+
+# ----------------------------------------------------------------------------------------------
+# row-sharded database over a torch.distributed group
+# ----------------------------------------------------------------------------------------------
+class ShardedDatabase:
+    """Database rows sharded across the ranks of a process group (one process per GPU).
+
+    Each rank searches its shard (global indices via idx_offset); the packed [nq, k] candidates are all-gathered
+    (NCCL over NVLink on GPUs; gloo in the CPU plumbing tests) and merged by rir_merge_topk on every rank."""
+
+    def __init__(self, local: Database, group=None):
+        import torch.distributed as dist
+        self.local = local
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def search(self, q_rows, q_scale, k: int, path: str = "auto"):
+        k_local = min(k, self.local.n)
+        sc, ix = self.local.search(q_rows, q_scale, k_local, path=path)
+        sc, ix = pad_topk(sc, ix, k)
+        if self.world == 1:
+            return sc, ix
+        all_s, all_i = gather_topk(sc, ix, self.world, self.group)
+        return merge_topk(all_s, all_i)
+
+
+def pad_topk(sc: torch.Tensor, ix: torch.Tensor, k: int):
+    """A shard shorter than k pads its list with (-inf, -1) so every rank contributes [nq, k]."""
+    have = sc.shape[1]
+    if have >= k:
+        return sc, ix
+    pad_s = torch.full((sc.shape[0], k - have), -math.inf, dtype=sc.dtype, device=sc.device)
+    pad_i = torch.full((ix.shape[0], k - have), -1, dtype=ix.dtype, device=ix.device)
+    return torch.cat([sc, pad_s], 1), torch.cat([ix, pad_i], 1)
+
+
+def gather_topk(sc: torch.Tensor, ix: torch.Tensor, world: int, group=None):
+    """The one exchange step of the sharded search: all-gather of the packed [nq, k] candidates
+    (nq*k*8 bytes per rank; NCCL over NVLink on GPUs, gloo in the CPU tests) -> ([G, nq, k], [G, nq, k])."""
+    import torch.distributed as dist
+    nq, k = sc.shape
+    all_s = torch.empty((world * nq, k), dtype=sc.dtype, device=sc.device)  # concatenated along dim 0 == [G, nq, k]
+    all_i = torch.empty((world * nq, k), dtype=ix.dtype, device=ix.device)
+    dist.all_gather_into_tensor(all_s, sc.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, ix.contiguous(), group=group)
+    return all_s.view(world, nq, k), all_i.view(world, nq, k)
+
+
+# ----------------------------------------------------------------------------------------------
+# alpha query expansion
+# ----------------------------------------------------------------------------------------------
+def alpha_query_expansion(db, q_rows, q_scale, scores, idx, kq: int = 10, alpha: float = 3.0, group=None):
+    """q' = L2(q + sum_{j<kq} max(s_j, 0)^alpha * x_{idx_j}); returns (q'_rows, q'_scale, q'_fp32).
+
+    `db` is a Database or ShardedDatabase; scores / idx are the (merged, global-index) top-k of the first pass."""
+    import torch.distributed as dist
+    local = db.local if isinstance(db, ShardedDatabase) else db
+    lib = _lib.load()
+    nq, d = q_rows.shape
+    kq = min(kq, scores.shape[1])
+    acc = torch.zeros((nq, d), dtype=torch.float32, device=q_rows.device)
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    dt = _DTYPES[local.dtype]
+    with torch.cuda.device(q_rows.device):
+        _lib.check(lib.rir_aqe_accumulate(local.rows.data_ptr(), dt, None if local.scale is None else local.scale.data_ptr(),
+                                          local.n, local.idx_offset, d, scores.data_ptr(), idx.data_ptr(), nq,
+                                          scores.shape[1], kq, float(alpha), acc.data_ptr(), _lib.stream_ptr()))
+    if isinstance(db, ShardedDatabase) and db.world > 1:
+        dist.all_reduce(acc, group=db.group)
+    out32 = torch.empty((nq, d), dtype=torch.float32, device=q_rows.device)
+    if local.dtype == "fp32":
+        out_q, out_scale = None, None
+    else:
+        out_q = torch.empty_like(q_rows)
+        out_scale = torch.empty(nq, dtype=torch.float32, device=q_rows.device)
+    with torch.cuda.device(q_rows.device):
+        _lib.check(lib.rir_aqe_finalize(q_rows.data_ptr(), dt, None if q_scale is None else q_scale.data_ptr(),
+                                        acc.data_ptr(), nq, d, out32.data_ptr(),
+                                        None if out_q is None else out_q.data_ptr(),
+                                        None if out_scale is None else out_scale.data_ptr(), _lib.stream_ptr()))
+    if local.dtype == "fp32":
+        return out32, None, out32
+    if local.dtype == "bf16":
+        out_scale = None
+    return out_q, out_scale, out32
+
+
+def search_with_aqe(db, q_rows, q_scale, k: int = 100, kq: int = 10, alpha: float = 3.0, path: str = "auto"):
+    """First-pass top-k -> alpha-QE -> second-pass top-k (BASELINE cfg-3).  Returns (scores, idx, q'_fp32)."""
+    sc, ix = db.search(q_rows, q_scale, k, path=path)
+    q2, q2s, q2f = alpha_query_expansion(db, q_rows, q_scale, sc, ix, kq=kq, alpha=alpha)
+    sc2, ix2 = db.search(q2, q2s, k, path=path)
+    return sc2, ix2, q2f
