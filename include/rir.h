@@ -121,6 +121,20 @@ int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, 
                  int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
                  void* workspace, size_t workspace_bytes, int path, void* stream);
 
+/* Measurement hook (bench.py's roofline): arm a pair of cudaEvent_t handles (passed as void*) that the following
+ * rir_sim_topk calls of THIS host thread record immediately before / after their full-scan kernel launch(es) on the
+ * call's stream.  Pass NULL, NULL to disarm.  The events must outlive the calls; timing is read by the caller. */
+int rir_profile_scan_events(void* ev_start, void* ev_stop);
+
+/* Re-score a candidate list with higher-precision rows and keep the best k (same order rule).  Used after an fp8
+ * scan that returned k_in > k candidates, so the final list meets the fp8 bar "5e-3 relative against an fp32 rescore".
+ *   Q[nq,d], X[n_local,d] in dtype RIR_BF16 or RIR_F32 (the rescoring copy of the shard); ix_in[nq,k_in] GLOBAL row
+ *   indices (-1 or rows outside [idx_offset, idx_offset+n_local) are skipped); out[nq,k], k <= k_in <= 8192.
+ * No reference counterpart (the reference only has fp32 rows). */
+int rir_rescore_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                     int64_t n_local, int64_t idx_offset, int d, const int32_t* ix_in, int k_in, int k,
+                     float* out_score, int32_t* out_idx, void* stream);
+
 /* k-way merge of G per-shard top-k lists sc/ix[G,nq,k] (as produced by an allgather of rir_sim_topk outputs)
  * into the global top-k (same order rule).  No reference counterpart. */
 size_t rir_merge_topk_workspace(int G, int nq, int k);

@@ -93,9 +93,11 @@ def alpha_qe(q: torch.Tensor, x: torch.Tensor, scores: np.ndarray, idx: np.ndarr
     return out
 
 
-def indices_match_up_to_ties(got_idx, got_sc, ref_idx, ref_sc, rel_eps: float):
-    """Bit-exact indices except inside near-tie groups: position j may differ only if the oracle scores of the two
-    candidates differ by <= rel_eps * |score|.  Returns (ok, message)."""
+def indices_match_up_to_ties(got_idx, got_sc, ref_idx, ref_sc, rel_eps: float, abs_eps: float = 2e-6):
+    """Bit-exact indices except inside near-tie groups: position j may differ only if the ORACLE scores of the two
+    candidates (got_sc = oracle score of the returned row) differ by <= rel_eps * |score| (north_star's bar), with an
+    absolute floor of abs_eps = 2e-6 for near-zero cosines in full rankings (fp32 accumulation-order noise of a
+    2048-term dot product of unit vectors).  Returns (ok, message)."""
     got_idx = np.asarray(got_idx).astype(np.int64)
     ref_idx = np.asarray(ref_idx).astype(np.int64)
     if got_idx.shape != ref_idx.shape:
@@ -103,7 +105,7 @@ def indices_match_up_to_ties(got_idx, got_sc, ref_idx, ref_sc, rel_eps: float):
     bad = np.argwhere(got_idx != ref_idx)
     for r, j in bad:
         a, b = float(got_sc[r, j]), float(ref_sc[r, j])
-        tol = rel_eps * max(abs(a), abs(b), 1e-30)
+        tol = max(rel_eps * max(abs(a), abs(b)), abs_eps)
         if abs(a - b) > tol:
             return False, f"query {r} position {j}: got idx {got_idx[r, j]} (score {a}) vs oracle {ref_idx[r, j]} (score {b})"
     return True, f"{len(bad)} tie swaps"

@@ -295,8 +295,9 @@ using namespace rir;
 extern "C" int rir_pool(const void* x, int dtype, int B, int C, int HW, int mode, float p, float eps, float alpha,
                         float beta, float* out, void* stream) {
   if (int e = check_arch()) return e;
-  RIR_REQUIRE(x && out, "pool: null pointer");
   RIR_REQUIRE(B >= 0 && C >= 1 && HW >= 1, "pool: bad shape B=%d C=%d HW=%d", B, C, HW);
+  if (B == 0) return RIR_OK;
+  RIR_REQUIRE(x && out, "pool: null pointer");
   RIR_REQUIRE(mode == RIR_POOL_GEM || mode == RIR_POOL_MAX || mode == RIR_POOL_AVG, "pool: bad mode %d", mode);
   RIR_REQUIRE(dtype == RIR_F32 || dtype == RIR_BF16, "pool: dtype must be f32 or bf16 (got %d)", dtype);
   RIR_REQUIRE(mode != RIR_POOL_GEM || p > 0.f, "pool: GeM exponent must be > 0 (got %g)", (double)p);

@@ -108,6 +108,15 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
 
 using namespace rir;
 
+// optional profiling hook: CUDA events recorded around the full-scan launch of the next rir_sim_topk calls
+static thread_local cudaEvent_t g_ev_scan_start = nullptr, g_ev_scan_stop = nullptr;
+
+extern "C" int rir_profile_scan_events(void* ev_start, void* ev_stop) {
+  g_ev_scan_start = (cudaEvent_t)ev_start;
+  g_ev_scan_stop = (cudaEvent_t)ev_stop;
+  return RIR_OK;
+}
+
 extern "C" int rir_version(void) { return RIR_VERSION; }
 extern "C" const char* rir_last_error(void) { return g_err; }
 extern "C" int rir_device_check(void) { return check_arch(); }
@@ -135,6 +144,7 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
   RIR_REQUIRE(k <= kMaxK, "sim_topk: k=%d exceeds %d", k, kMaxK);
   RIR_REQUIRE(((size_t)d * esz) % 16 == 0, "sim_topk: row size %zu B must be a multiple of 16 (pad d with zeros)",
               (size_t)d * esz);
+  if (nq == 0) return RIR_OK;
   RIR_REQUIRE(out_score && out_idx, "sim_topk: null output");
   RIR_REQUIRE(n_local + idx_offset < (1ll << 31) && idx_offset >= 0, "sim_topk: global row index exceeds int32");
   RIR_REQUIRE(path >= RIR_PATH_AUTO && path <= RIR_PATH_EXACT, "sim_topk: bad path %d", path);
@@ -206,13 +216,17 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     p.nq = gq;
     if (pl.scan_all) {
       // every row is a candidate: slot == row, cnt = n set by the select kernel's launch parameters
+      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
       if (int e = run_pass(kModeScanAll)) return e;
+      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
       p.mode = kModeScanAll;
     } else {
       if (int e = run_pass(kModeSample)) return e;
       if (int e = launch_sample_threshold(p, gq, k, st)) return e;
       RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (size_t)gq * sizeof(uint32_t), st));
+      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
       if (int e = run_pass(kModeScanFilter)) return e;
+      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
       p.mode = kModeScanFilter;
     }
     float* os = out_score + (size_t)g0 * k;

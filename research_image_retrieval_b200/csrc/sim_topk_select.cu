@@ -240,6 +240,52 @@ int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long l
 }
 
 // ---------------------------------------------------------------------------------------------
+// rescore: recompute the scores of a candidate list with higher-precision rows (bf16 / fp32) and keep the best k.
+// Used after an fp8 scan (k_in > k candidates with margin) so the final list meets the 5e-3 bar against an fp32
+// rescore (BASELINE.json north_star; SURVEY.md §7.3 "fp8 quantisation of unit-norm vectors").
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kExactThreads)
+    rescore_kernel(const void* Q, const void* X, const float* q_scale, const float* x_scale, long long n_local,
+                   long long idx_offset, int d, const int32_t* ix_in, int k_in, int k, int kpad, float* out_sc,
+                   int32_t* out_ix) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);       // [kin_pad]
+  const int kin_pad = pow2_ceil_int(k_in < 32 ? 32 : k_in);
+  uint64_t* dst = keys + kin_pad;                                // [kpad]
+  float* qs = reinterpret_cast<float*>(dst + kpad);              // [d]
+  __shared__ SelectScratch scr;
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ESZ = DT == RIR_F32 ? 4 : (DT == RIR_BF16 ? 2 : 1);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float v;
+    if (DT == RIR_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(Q)[(size_t)q * d + i]);
+    else v = reinterpret_cast<const float*>(Q)[(size_t)q * d + i];
+    if (q_scale) v *= q_scale[q];
+    qs[i] = v;
+  }
+  __syncthreads();
+  const int chunks = (d * ESZ) >> 4;
+  for (int j = warp; j < k_in; j += kExactThreads / 32) {
+    const long long gid = ix_in[(size_t)q * k_in + j];
+    const long long loc = gid - idx_offset;
+    unsigned long long key = 0ull;
+    if (gid >= 0 && loc >= 0 && loc < n_local) {
+      float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(X) + (size_t)loc * d * ESZ, qs, chunks, lane);
+      if (x_scale) s *= x_scale[loc];
+      key = make_key(s, (uint32_t)loc);
+    }
+    if (lane == 0) keys[j] = key;
+  }
+  __syncthreads();
+  const uint64_t* kk = keys;
+  auto key_at = [=](int i) -> unsigned long long { return kk[i]; };
+  const int got = block_select_topk(key_at, k_in, k, dst, kpad, &scr);
+  write_sorted(dst, got, k, idx_offset, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+}
+
+// ---------------------------------------------------------------------------------------------
 // cross-shard merge: [G, nq, k] sorted lists -> global top-k
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelectThreads)
@@ -260,6 +306,36 @@ __global__ void __launch_bounds__(kSelectThreads)
 }
 
 }  // namespace rir
+
+extern "C" int rir_rescore_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale,
+                                int nq, int64_t n_local, int64_t idx_offset, int d, const int32_t* ix_in, int k_in,
+                                int k, float* out_score, int32_t* out_idx, void* stream) {
+  using namespace rir;
+  if (int e = check_arch()) return e;
+  RIR_REQUIRE(nq >= 0 && d >= 1 && k >= 1 && k_in >= k && k_in <= 8192, "rescore_topk: bad shape nq=%d k_in=%d k=%d", nq,
+              k_in, k);
+  RIR_REQUIRE(dtype == RIR_BF16 || dtype == RIR_F32, "rescore_topk: rescoring rows must be bf16 or fp32");
+  const int esz = dtype == RIR_BF16 ? 2 : 4;
+  RIR_REQUIRE(((size_t)d * esz) % 16 == 0, "rescore_topk: row size must be a multiple of 16 bytes");
+  if (nq == 0) return RIR_OK;
+  RIR_REQUIRE(Q && X && ix_in && out_score && out_idx, "rescore_topk: null pointer");
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const int kin_pad = pow2_ceil_int(k_in < 32 ? 32 : k_in);
+  const size_t smem = (size_t)(kpad + kin_pad) * sizeof(uint64_t) + (size_t)d * sizeof(float);
+  RIR_REQUIRE(smem <= 220 * 1024, "rescore_topk: k_in/k/d too large for shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RIR_BF16) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(rescore_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rescore_kernel<RIR_BF16><<<nq, kExactThreads, smem, st>>>(Q, X, q_scale, x_scale, n_local, idx_offset, d, ix_in, k_in, k,
+                                                             kpad, out_score, out_idx);
+  } else {
+    RIR_CUDA_OK(cudaFuncSetAttribute(rescore_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rescore_kernel<RIR_F32><<<nq, kExactThreads, smem, st>>>(Q, X, q_scale, x_scale, n_local, idx_offset, d, ix_in, k_in, k,
+                                                            kpad, out_score, out_idx);
+  }
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}
 
 extern "C" size_t rir_merge_topk_workspace(int G, int nq, int k) {
   (void)G; (void)nq; (void)k;

@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) sim_stream_kernel(const Sim
             p.sample_scores[(size_t)(p.q0 + q) * ((size_t)p.sblk * kSampleBlockRows) + pos] =
                 valid ? score : -INFINITY;
           } else if (valid) {
-            if (p.mode == kModeScanAll || passes(score, (uint32_t)row, ts[q], ti[q]))
+            if (p.mode == kModeScanAll)  // slot == row (cap >= n): no atomics, the select kernel reads n entries
+              p.cand[(size_t)(p.q0 + q) * p.cap + (size_t)row] = make_key(score, (uint32_t)row);
+            else if (passes(score, (uint32_t)row, ts[q], ti[q]))
               push_candidate(p, p.q0 + q, score, (uint32_t)row);
           }
         }

@@ -118,19 +118,28 @@ class Database:
     idx_offset: global index of local row 0."""
 
     def __init__(self, rows: torch.Tensor, scale: Optional[torch.Tensor], dtype: str, idx_offset: int = 0,
-                 d_logical: Optional[int] = None):
+                 d_logical: Optional[int] = None, rescore_rows: Optional[torch.Tensor] = None):
         self.rows, self.scale, self.dtype, self.idx_offset = rows, scale, dtype, int(idx_offset)
         self.n, self.d = rows.shape
         self.d_logical = d_logical or self.d
+        self.rescore_rows = rescore_rows  # bf16 copy of the shard used to re-score fp8 candidates
         self._ws = None
 
     @classmethod
-    def from_descriptors(cls, v: torch.Tensor, dtype: str = "bf16", idx_offset: int = 0, normalize: bool = False):
+    def from_descriptors(cls, v: torch.Tensor, dtype: str = "bf16", idx_offset: int = 0, normalize: bool = False,
+                         rescore: bool = False):
+        """rescore=True (fp8 only) also keeps a bf16 copy: the fp8 scan returns 2k+16 candidates which are re-scored
+        against it, so the final top-k meets the 5e-3 bar against an fp32 rescore."""
         if normalize:
             from .pooling import l2n
             v = l2n(v.float().contiguous())
         rows, scale = pack_descriptors(v, dtype)
-        return cls(rows, scale, dtype, idx_offset, d_logical=v.shape[1])
+        rs = None
+        if rescore and dtype == "fp8":
+            rs, _ = pack_descriptors(v, "bf16")
+            if rs.shape[1] != rows.shape[1]:  # fp8 rows pad d to 16, bf16 to 8: use the common padded width
+                rs = torch.nn.functional.pad(rs, (0, rows.shape[1] - rs.shape[1]))
+        return cls(rows, scale, dtype, idx_offset, d_logical=v.shape[1], rescore_rows=rs)
 
     def pack_queries(self, q: torch.Tensor):
         """fp32 [nq, d_logical] -> the shard's dtype (padded like the rows)."""
@@ -150,6 +159,27 @@ class Database:
         """Exact local top-k.  Returns (scores [nq, k] fp32, idx [nq, k] int32 GLOBAL indices) on the GPU."""
         return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
                         idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k))
+
+    def query(self, q: torch.Tensor, k: int, path: str = "auto"):
+        """fp32 queries [nq, d_logical] -> top-k.  With a rescoring copy: fp8 scan for 2k+16 candidates, then a bf16
+        re-score of those rows (rir_rescore_topk) decides the final k."""
+        q = q.to(self.rows.device).float()
+        qr, qs = self.pack_queries(q)
+        if self.rescore_rows is None:
+            return self.search(qr, qs, k, path=path)
+        k_in = min(self.n, 2 * k + 16, 8192)
+        _, cand = self.search(qr, qs, k_in, path=path)
+        qb, _ = pack_descriptors(q, "bf16")
+        if qb.shape[1] != self.rescore_rows.shape[1]:
+            qb = torch.nn.functional.pad(qb, (0, self.rescore_rows.shape[1] - qb.shape[1]))
+        sc = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+        ix = torch.empty((q.shape[0], k), dtype=torch.int32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.load().rir_rescore_topk(qb.data_ptr(), self.rescore_rows.data_ptr(), RIR_BF16, None, None,
+                                                    q.shape[0], self.n, self.idx_offset, self.rescore_rows.shape[1],
+                                                    cand.data_ptr(), k_in, k, sc.data_ptr(), ix.data_ptr(),
+                                                    _lib.stream_ptr()))
+        return sc, ix
 
 
 def sim_topk(Q: torch.Tensor, X: torch.Tensor, k: int, dtype: str = "bf16", q_scale=None, x_scale=None,

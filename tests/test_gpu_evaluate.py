@@ -1,0 +1,154 @@
+"""GPU parity: revisited mAP kernel (through the C ABI) — bit-exact against the reference's golden outputs and the oracle."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+import research_image_retrieval_b200 as rir
+from conftest import csr_to_lists, load_golden
+from oracle import evaluate_oracle as E
+from oracle import search_oracle as S
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gnd(g, keys):
+    n = len(g[f"{keys[0]}_off"]) - 1
+    lists = {k: csr_to_lists(g[f"{k}_ids"], g[f"{k}_off"]) for k in keys}
+    return [{k: lists[k][i] for k in keys} for i in range(n)]
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))  # bit-exact fp64
+
+
+def test_golden_full_ranking_bit_exact(cuda_device):
+    g = load_golden("map_full")
+    gnd = _gnd(g, ["easy", "hard", "junk"])
+    res = rir.revisited_map(g["ranks"], gnd, [1, 5, 10])
+    for name, (m, aps, pr, prs) in zip("EMH", res):
+        assert m == float(g[f"map_{name}"])
+        np.testing.assert_array_equal(aps, g[f"aps_{name}"])
+        np.testing.assert_array_equal(pr, g[f"pr_{name}"])
+        np.testing.assert_array_equal(prs, g[f"prs_{name}"])
+    for name, gt in zip("EMH", E.revisited_gnd(gnd)):
+        m, aps = rir.compute_map(g["ranks"], gt)
+        assert m == float(g[f"map_nokeep_{name}"])
+        np.testing.assert_array_equal(aps, g[f"aps_nokeep_{name}"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        out = rir.compute_map_and_print("roxford5k", "golden", "global", g["ranks"], gnd, [1, 5, 10], True)
+    assert tuple(float(x) for x in out) == (float(g["mapE"]), float(g["mapM"]), float(g["mapH"]))
+    assert buf.getvalue() == str(g["text"])  # the printed report is part of the drop-in contract
+
+
+def test_golden_truncated_and_ragged(cuda_device):
+    g = load_golden("map_truncated")
+    gnd = _gnd(g, ["ok", "junk"])
+    m, aps = rir.compute_map(g["ranks"], gnd)
+    assert m == float(g["map"])
+    np.testing.assert_array_equal(aps, g["aps"])
+    off = np.concatenate([[0], np.cumsum(g["ragged_len"])])
+    ragged = [list(g["ragged_flat"][off[i]:off[i + 1]]) for i in range(len(gnd))]
+    m, aps = rir.compute_map(ragged, gnd, li=True)
+    assert m == float(g["map_li"])
+    np.testing.assert_array_equal(aps, g["aps_li"])
+
+
+def test_known_answers(cuda_device):
+    g = load_golden("map_kat")
+    assert rir.compute_ap([0, 1, 2], 3) == float(g["ap_012_3"]) == 1.0
+    assert rir.compute_ap([1, 3], 2) == float(g["ap_13_2"])
+    assert rir.compute_ap([], 4) == 0.0
+    out = rir.compute_map(np.arange(10).reshape(10, 1), [{"ok": [0, 3], "junk": [1]}], [1, 5])
+    _same(out, (g["k1_map"], g["k1_aps"], g["k1_pr"], g["k1_prs"]))
+    out = rir.compute_map(np.array([[3], [9], [1], [4]]), [{"ok": [1, 2], "junk": [9]}], [1, 5])
+    _same(out, (g["k2_map"], g["k2_aps"], g["k2_pr"], g["k2_prs"]))
+    out = rir.compute_map(np.array([[0, 0], [1, 1]]), [{"ok": []}, {"ok": [0]}], [1])
+    _same(out, (g["k3_map"], g["k3_aps"], g["k3_pr"], g["k3_prs"]))
+    out = rir.compute_map(np.array([[0], [1]]), [{"ok": [1]}])  # missing 'junk' key tolerated
+    _same(out, (g["k4_map"], g["k4_aps"]))
+    out = rir.compute_map([[5, 6, 7]], [{"ok": [1], "junk": []}], li=True)
+    _same(out, (g["k5_map"], g["k5_aps"]))
+
+
+def test_reference_exceptions(cuda_device):
+    with pytest.raises(ValueError, match="max"):  # keeps + no positive retrieved (utils/evaluate.py:101)
+        rir.compute_map([[5, 6, 7]], [{"ok": [1], "junk": []}], [1], li=True)
+    with pytest.raises(ZeroDivisionError):       # every query without positives (utils/evaluate.py:105)
+        rir.compute_map(np.array([[0], [1]]), [{"ok": []}])
+    with pytest.raises(ValueError):              # old protocol branch unpacks 4 from 2 (utils/evaluate.py:157)
+        rir.compute_map_and_print("oxford5k", "x", "y", np.arange(4).reshape(4, 1), [{"ok": [1], "junk": []}])
+    assert rir.compute_map_and_print("unknown", "x", "y", np.arange(4).reshape(4, 1), []) is None
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_cases_vs_oracle(cuda_device, seed):
+    rng = np.random.RandomState(seed)
+    nq, n = 23, 1300  # > 256 positions: several chunks with running offsets
+    ranks = np.stack([rng.permutation(n) for _ in range(nq)], axis=1)
+    gnd = synth.revisited_gnd(nq, n, seed=seed + 50, n_empty_easy=3)
+    if seed == 3:  # overlapping ok/junk ids and duplicate ok ids behave like np.in1d + len(ok)
+        gnd[5]["junk"] = np.concatenate([gnd[5]["junk"], gnd[5]["easy"][:3]])
+        gnd[6]["hard"] = np.concatenate([gnd[6]["hard"], gnd[6]["hard"][:2]])
+    for L in (n, 300, 17):
+        try:
+            want = E.compute_map_revisited(ranks[:L], gnd, [1, 5, 10, 100])
+        except ValueError:
+            with pytest.raises(ValueError):
+                rir.revisited_map(ranks[:L], gnd, [1, 5, 10, 100])
+            continue
+        got = rir.revisited_map(ranks[:L], gnd, [1, 5, 10, 100])
+        for a, b in zip(got, want):
+            _same(a, b)
+    # torch tensors on the device are accepted as-is
+    got = rir.revisited_map(torch.from_numpy(ranks).to(cuda_device), gnd, [1, 5, 10])
+    for a, b in zip(got, E.compute_map_revisited(ranks, gnd, [1, 5, 10])):
+        _same(a, b)
+
+
+def test_cfg1_end_to_end_roxford_shape(cuda_device):
+    """BASELINE cfg-1: 70 x 4,993 x 2048 fp32, full ranking + revisited mAP, against the reference path restated on CPU.
+    E/M/H (2-dp) must be identical; unrounded mAP within 1e-4 (ranking ties at fp32 rounding level may differ)."""
+    nq, n, d = 70, 4993, 2048
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=1001)
+    gnd = synth.revisited_gnd(nq, n, seed=1001)
+    ref_ranks = S.full_rank(Q, X).T  # [n, nq]
+    want = E.compute_map_revisited(ref_ranks, gnd)
+    ranks = rir.rank(Q, X)           # fp32 path, [n, nq] int64
+    assert ranks.shape == (n, nq)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        e, m, h = rir.compute_map_and_print("roxford5k", "synthetic", "global", ranks, gnd)
+    assert (e, m, h) == E.compute_map_and_print_values(ref_ranks, gnd)
+    got = rir.revisited_map(ranks, gnd)
+    for a, b in zip(got, want):
+        assert abs(a[0] - b[0]) <= 1e-4
+    # and on identical rankings the kernel is bit-exact
+    for a, b in zip(rir.revisited_map(ref_ranks, gnd), want):
+        _same(a, b)
+    # bf16 database: mAP within 1e-4 of the fp32 reference path on the de-quantised inputs
+    Xb, Qb = X.to(torch.bfloat16).float(), Q.to(torch.bfloat16).float()
+    want_b = E.compute_map_revisited(S.full_rank(Qb, Xb).T, gnd)
+    got_b = rir.revisited_map(rir.rank(Q, X, dtype="bf16"), gnd)
+    for a, b in zip(got_b, want_b):
+        assert abs(a[0] - b[0]) <= 1e-4
+
+
+def test_truncated_topk_from_search_feeds_map(cuda_device):
+    """top-100 lists straight from the search kernel (device tensor, [k, nq]) into the mAP kernel."""
+    nq, n, d = 16, 30000, 256
+    Q, X, planted = synth.retrieval_set(nq, n, d, seed=7)
+    gnd = [{"ok": planted[i], "junk": np.array([int(planted[(i + 1) % nq][0])])} for i in range(nq)]
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, 100)
+    m, aps = rir.compute_map(ix.t(), gnd)
+    m2, aps2 = E.compute_map(ix.t().cpu().numpy(), gnd)
+    assert m == m2 == 1.0
+    np.testing.assert_array_equal(aps, aps2)

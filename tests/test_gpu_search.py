@@ -1,0 +1,278 @@
+"""GPU parity: similarity + top-k (+ merge, alpha-QE) through the C ABI vs the fp32 oracle on de-quantised inputs.
+
+Bar (BASELINE.json north_star): indices bit-exact except ties within 1e-3 relative (bf16) / 5e-3 relative (fp8,
+against an fp32 rescore).  fp32 descriptors: indices exact except fp32-rounding ties (1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+import research_image_retrieval_b200 as rir
+from conftest import load_golden
+from oracle import descriptor_oracle as D
+from oracle import search_oracle as S
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+EPS = {"fp32": 1e-5, "bf16": 1e-3, "fp8": 5e-3}
+
+
+def _dequant(rows, scale, dtype):
+    r = rows.cpu()
+    if dtype == "fp8":
+        r = r.view(torch.float8_e4m3fn).float() * scale.cpu()[:, None]
+    return r.float()
+
+
+def _check(got_sc, got_ix, Qf, Xf, k, eps, idx_offset=0):
+    """got vs oracle on the same (de-quantised) fp32 inputs."""
+    ref_sc, ref_ix = S.topk(Qf, Xf, k, idx_offset=idx_offset)
+    got_ix = got_ix.cpu().numpy().astype(np.int64)
+    got_sc = got_sc.cpu().numpy()
+    assert got_ix.shape == ref_ix.shape
+    # the scores we return must be the fp32 dot products of the rows we return
+    sim_of_got = np.stack([(Xf[torch.from_numpy(got_ix[r] - idx_offset)] @ Qf[r]).numpy() for r in range(Qf.shape[0])])
+    np.testing.assert_allclose(got_sc, sim_of_got, rtol=2e-4, atol=2e-6)
+    ok, msg = S.indices_match_up_to_ties(got_ix, sim_of_got, ref_ix, ref_sc, eps)
+    assert ok, msg
+    # rows come out in non-increasing score order, and each index appears once
+    assert np.all(np.diff(got_sc, axis=1) <= 0)
+    for r in range(got_ix.shape[0]):
+        assert len(set(got_ix[r].tolist())) == k
+    return msg
+
+
+CASES = [
+    # nq, n, d, k
+    (1, 5000, 2048, 100),      # scan-all (n <= 16384), 1 query
+    (3, 20011, 512, 100),      # filtered scan, n not a multiple of 256
+    (4, 70000, 256, 10),
+    (8, 33000, 128, 17),
+    (70, 4993, 2048, 4993),    # cfg-1 shape: full ranking
+    (70, 50000, 1024, 100),    # cfg-2 shape scaled down
+    (130, 40000, 256, 50),     # two query blocks on the MMA path
+    (5, 18000, 72, 5),         # d not a multiple of the 128-byte K chunk
+    (2, 300, 64, 300),         # tiny database, full ranking
+]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp8", "fp32"])
+@pytest.mark.parametrize("path", ["stream", "mma", "exact"])
+@pytest.mark.parametrize("nq,n,d,k", CASES)
+def test_sim_topk_paths(cuda_device, dtype, path, nq, n, d, k):
+    if dtype == "fp32" and path == "mma":
+        pytest.skip("fp32 descriptors run on the CUDA-core paths only")
+    if path == "exact" and nq * n * d > 4e9:
+        pytest.skip("exact path is the slow fallback; covered at smaller sizes")
+    Q, X, planted = synth.retrieval_set(nq, n, d, seed=n + d + nq)
+    db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k, path=path)
+    torch.cuda.synchronize()
+    Xf = _dequant(db.rows, db.scale, dtype)[:, :d]
+    Qf = _dequant(qr, qs, dtype)[:, :d]
+    _check(sc, ix, Qf, Xf, k, EPS[dtype] if dtype != "fp8" else 1e-3)  # vs the de-quantised oracle: accumulate-order only
+    if planted.shape[1] and k >= planted.shape[1] and dtype != "fp8":
+        got = ix.cpu().numpy()
+        for r in range(nq):
+            assert set(planted[r].tolist()) <= set(got[r, : max(k, planted.shape[1])].tolist())
+
+
+def test_fp8_against_fp32_rescore(cuda_device):
+    """fp8 bar (north_star): indices exact except ties within 5e-3 relative, judged on TRUE fp32 scores.  The fp8 scan
+    over-fetches 2k+16 candidates and a bf16 re-score of those rows decides the final order."""
+    nq, n, d, k = 16, 30000, 512, 8
+    Q, X, planted = synth.retrieval_set(nq, n, d, seed=123, n_pos=8)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "fp8", rescore=True)
+    sc, ix = db.query(Q.to(cuda_device), k)
+    ref_sc, ref_ix = S.topk(Q, X, k)
+    got = ix.cpu().numpy().astype(np.int64)
+    true_of_got = np.stack([(X[torch.from_numpy(got[r])] @ Q[r]).numpy() for r in range(nq)])
+    ok, msg = S.indices_match_up_to_ties(got, true_of_got, ref_ix, ref_sc, 5e-3)
+    assert ok, msg
+    np.testing.assert_allclose(sc.cpu().numpy(), true_of_got, rtol=5e-3)
+    for r in range(nq):
+        assert set(got[r].tolist()) == set(planted[r].tolist())
+    # random (non-planted) neighbours, k=100: same bar
+    sc, ix = db.query(Q.to(cuda_device), 100)
+    ref_sc, ref_ix = S.topk(Q, X, 100)
+    got = ix.cpu().numpy().astype(np.int64)
+    true_of_got = np.stack([(X[torch.from_numpy(got[r])] @ Q[r]).numpy() for r in range(nq)])
+    ok, msg = S.indices_match_up_to_ties(got, true_of_got, ref_ix, ref_sc, 5e-3)
+    assert ok, msg
+
+
+def test_auto_path_and_grouping(cuda_device):
+    Q, X, _ = synth.retrieval_set(9, 21000, 64, seed=3)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    a = db.search(qr, qs, 20, path="auto")
+    b = db.search(qr, qs, 20, path="stream")  # 9 queries -> two stream launches of 8 + 1
+    c = db.search(qr[:3].contiguous(), None, 20, path="auto")  # <= 4 queries -> stream
+    assert torch.equal(a[1], b[1]) and torch.equal(a[1][:3], c[1])
+    np.testing.assert_allclose(a[0].cpu().numpy(), b[0].cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_exact_ties_ascending_index(cuda_device):
+    """Duplicate rows have bit-identical scores on every path: they must come out in ascending index order."""
+    Q, X, _ = synth.retrieval_set(2, 17000, 128, seed=8)
+    dup = [16999, 5, 9000, 777]
+    for i in dup:
+        X[i] = Q[0]
+    for dtype, paths in [("bf16", ["stream", "mma", "exact"]), ("fp32", ["stream", "exact"])]:
+        db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+        qr, qs = db.pack_queries(Q.to(cuda_device))
+        for path in paths:
+            sc, ix = db.search(qr, qs, 6, path=path)
+            assert ix[0, :4].cpu().tolist() == sorted(dup), (dtype, path)
+            assert float(sc[0, 0]) == float(sc[0, 3])
+
+
+def _sampled_blocks(n):
+    nblk = -(-n // 256)
+    sblk = max(74, int(0.02 * nblk + 0.5))
+    sblk = min(sblk, nblk - 1)
+    return {(j * nblk) // sblk for j in range(sblk)}, nblk
+
+
+@pytest.mark.parametrize("path", ["stream", "mma"])
+def test_candidate_overflow_falls_back_to_exact_scan(cuda_device, path):
+    """Adversarial row order: thousands of rows beating everything in the strided sample sit in un-sampled blocks, so
+    the candidate list overflows and the one-CTA-per-query fallback must take over.  Result must still be exact."""
+    n, d, k = 200000, 64, 10
+    Q, X, _ = synth.retrieval_set(2, n, d, seed=99, n_pos=0)
+    sampled, nblk = _sampled_blocks(n)
+    free = [b for b in range(nblk - 1) if b not in sampled]
+    rows = np.concatenate([np.arange(b * 256, b * 256 + 256) for b in free[:24]])  # 6144 rows > cap (2048)
+    gen = torch.Generator().manual_seed(5)
+    near = Q[0][None, :] + torch.randn(len(rows), d, generator=gen) * (0.3 / d ** 0.5)
+    X[torch.from_numpy(rows)] = near / near.norm(dim=1, keepdim=True)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k, path=path)
+    Xf, Qf = db.rows.float().cpu(), qr.float().cpu()
+    _check(sc, ix, Qf, Xf, k, 1e-3)
+    assert set(ix[0].cpu().tolist()) <= set(rows.tolist())
+
+
+def test_rank_dropin_golden(cuda_device):
+    """rank() against the reference call site run verbatim (iris_evaluate.py:379-386) on the golden inputs."""
+    g = load_golden("ranking")
+    ranks = rir.rank(g["q"], g["g"], normalize=True)            # fp32, full ranking, [N, nq] int64
+    assert ranks.dtype == np.int64 and ranks.shape == (300, 6)
+    ours = np.take_along_axis(g["sim"], ranks.T, 1)
+    theirs = np.take_along_axis(g["sim"], g["ranks"], 1)
+    np.testing.assert_allclose(ours, theirs, rtol=0, atol=2e-7)  # same order up to fp32-rounding ties
+    top = rir.rank(g["q"], g["g"], k=10, normalize=True)
+    np.testing.assert_array_equal(top.T, g["topk_idx"])
+    r2, s2 = rir.rank(g["q"], g["g"], k=10, normalize=True, return_scores=True)
+    np.testing.assert_allclose(s2.T, g["topk_scores"], rtol=1e-5)
+
+
+def test_merge_and_single_gpu_shard_emulation(cuda_device):
+    """Row-sharded search emulated on one GPU: 3 shards with idx_offset -> merge_topk == unsharded search."""
+    nq, n, d, k = 7, 60000, 128, 100
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=17)
+    Xd, Qd = X.to(cuda_device), Q.to(cuda_device)
+    whole = rir.Database.from_descriptors(Xd, "bf16")
+    qr, qs = whole.pack_queries(Qd)
+    want_sc, want_ix = whole.search(qr, qs, k)
+    parts_s, parts_i = [], []
+    for r in range(3):
+        lo, hi = rir.shard_bounds(n, 3, r)
+        sh = rir.Database.from_descriptors(Xd[lo:hi], "bf16", idx_offset=lo)
+        s, i = sh.search(qr, qs, k)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = rir.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, want_ix)
+    assert torch.equal(ms, want_sc)
+    # padding entries (-inf, -1) from a short shard are ignored
+    parts_s[2][:, 50:] = float("-inf")
+    parts_i[2][:, 50:] = -1
+    ms2, mi2 = rir.merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    os_, oi = S.merge_shards([p.cpu().numpy() for p in parts_s], [p.cpu().numpy() for p in parts_i], k)
+    np.testing.assert_array_equal(mi2.cpu().numpy(), oi)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_alpha_query_expansion(cuda_device, dtype):
+    nq, n, d, k, kq, alpha = 12, 25000, 256, 50, 10, 3.0
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=31)
+    db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k)
+    q2, q2s, q2f = rir.alpha_query_expansion(db, qr, qs, sc, ix, kq=kq, alpha=alpha)
+    Xf, Qf = db.rows.float().cpu(), qr.float().cpu()
+    want = S.alpha_qe(Qf, Xf, sc.cpu().numpy(), ix.cpu().numpy(), kq, alpha)
+    np.testing.assert_allclose(q2f.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
+    sc2, ix2, _ = rir.search_with_aqe(db, qr, qs, k=k, kq=kq, alpha=alpha)
+    _check(sc2, ix2, q2.float().cpu(), Xf, k, EPS[dtype])
+    # sharded accumulate: two half-shards, partial sums added by hand == unsharded
+    lo, hi = rir.shard_bounds(n, 2, 1)
+    a = rir.Database(db.rows[:lo], None, dtype, 0)
+    b = rir.Database(db.rows[lo:], None, dtype, lo)
+    lib = rir.load()
+    from research_image_retrieval_b200 import _lib
+    acc = torch.zeros(nq, d, device=cuda_device)
+    for part in (a, b):
+        _lib.check(lib.rir_aqe_accumulate(part.rows.data_ptr(), _lib.RIR_BF16 if dtype == "bf16" else _lib.RIR_F32, None,
+                                          part.n, part.idx_offset, d, sc.data_ptr(), ix.data_ptr(), nq, k, kq, alpha,
+                                          acc.data_ptr(), None))
+    torch.cuda.synchronize()
+    v = Qf.to(cuda_device) + acc
+    np.testing.assert_allclose((v / v.norm(dim=1, keepdim=True)).cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_argument_errors(cuda_device):
+    X = torch.zeros(100, 64, device=cuda_device, dtype=torch.bfloat16)
+    Q = torch.zeros(2, 64, device=cuda_device, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        rir.sim_topk(Q, X, 0)
+    with pytest.raises(ValueError):
+        rir.sim_topk(Q, X, 101)
+    with pytest.raises(ValueError):
+        rir.sim_topk(Q[:, :32].contiguous(), X, 5)
+    with pytest.raises(rir.RirError):  # 68 bf16 = 136 B rows: not a multiple of 16
+        rir.sim_topk(torch.zeros(2, 68, device=cuda_device, dtype=torch.bfloat16),
+                     torch.zeros(100, 68, device=cuda_device, dtype=torch.bfloat16), 5)
+    with pytest.raises(rir.RirError):  # workspace too small
+        rir.sim_topk(Q, X, 5, workspace=torch.zeros(256, dtype=torch.uint8, device=cuda_device))
+    sc, ix = rir.sim_topk(Q[:0].contiguous(), X, 5)  # empty query batch is a no-op
+    assert tuple(sc.shape) == (0, 5)
+
+
+@pytest.mark.parametrize("nq,path", [(1, "stream"), (70, "mma")])
+def test_full_size_properties(cuda_device, nq, path):
+    """BASELINE cfg-2 size (1,007,323 x 2048 bf16, top-100): size-independent properties + a GPU fp32 rescore."""
+    n, d, k = 1007323, 2048, 100
+    gen = torch.Generator(device=cuda_device).manual_seed(1002)
+    X = torch.empty(n, d, device=cuda_device, dtype=torch.bfloat16)
+    for lo in range(0, n, 65536):
+        blk = torch.randn(min(65536, n - lo), d, generator=gen, device=cuda_device)
+        X[lo:lo + blk.shape[0]] = (blk / blk.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    Q = torch.randn(nq, d, generator=gen, device=cuda_device)
+    Q = Q / Q.norm(dim=1, keepdim=True)
+    planted = torch.randperm(n, generator=gen, device=cuda_device)[: nq * 5].reshape(nq, 5)
+    for r in range(nq):
+        rows = Q[r][None] + torch.randn(5, d, generator=gen, device=cuda_device) * (0.5 / d ** 0.5)
+        X[planted[r]] = (rows / rows.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    db = rir.Database(X, None, "bf16")
+    qr = Q.to(torch.bfloat16)
+    sc, ix = db.search(qr, None, k, path=path)
+    torch.cuda.synchronize()
+    ixl = ix.long()
+    # (1) planted near-duplicates lead the list; (2) sorted; (3) unique; (4) returned scores == fp32 rescore
+    for r in range(nq):
+        assert set(planted[r].tolist()) == set(ixl[r, :5].tolist())
+        assert len(set(ixl[r].tolist())) == k
+    assert bool((sc[:, 1:] <= sc[:, :-1]).all())
+    rescored = torch.einsum("qkd,qd->qk", X[ixl].float(), qr.float())
+    assert torch.allclose(sc, rescored, rtol=2e-4, atol=2e-6)
+    # (5) exactness: nothing outside the list beats the k-th score by more than the bf16 tie epsilon
+    kth = sc[:, -1]
+    for lo in range(0, n, 131072):
+        s = qr.float() @ X[lo:lo + 131072].float().t()
+        better = s > (kth * (1 + 1e-3))[:, None]
+        cnt = better.sum(1)
+        inlist = ((ixl >= lo) & (ixl < lo + 131072) & (sc > (kth * (1 + 1e-3))[:, None])).sum(1)
+        assert torch.equal(cnt, inlist)
