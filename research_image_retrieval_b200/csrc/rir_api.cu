@@ -82,7 +82,8 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
     if (k > kMaxKFilter) return false;
     pl->scan_all = false;
     long long sblk = (long long)(0.02 * pl->nblk + 0.5);
-    if (sblk < 74) sblk = 74;                        // half a wave of 256-row tiles
+    if (sblk < 32) sblk = 32;                        // >= 8192 sampled rows
+    if (sblk > 148) sblk = 148;                      // one tile per SM is plenty: ~k*n/37888 survivors
     const long long need = (4ll * k + kSampleBlockRows - 1) / kSampleBlockRows;
     if (sblk < need) sblk = need;
     if (sblk > pl->nblk - 1) sblk = pl->nblk - 1;    // the last block may be partial: never sample it

@@ -22,16 +22,16 @@ __global__ void __launch_bounds__(kSelectThreads) sample_threshold_kernel(const 
   const int m = p.sblk * kSampleBlockRows;
   const float* s = p.sample_scores + (size_t)q * m;
   const int nblk = p.nblk, sblk = p.sblk;
-  auto key_at = [=](int i) -> unsigned long long {
-    const long long row = sample_block_row0(i / kSampleBlockRows, nblk, sblk) + (i % kSampleBlockRows);
-    return make_key(s[i], (uint32_t)row);
-  };
+  // sample position i is monotonic in the database row index, so it can stand in for the row inside the key
+  // (no 64-bit division per access); only the selected k-th key is mapped back to its row.
+  auto key_at = [=](int i) -> unsigned long long { return make_key(s[i], (uint32_t)i); };
   const int got = block_select_topk(key_at, m, k, dst, kpad, &sc);
   if (threadIdx.x == 0) {
     // got == k whenever the host sized the sample (S >= k valid rows); otherwise fall back to "accept everything"
     if (got >= k && key_score(dst[k - 1]) > -INFINITY) {
+      const int pos = (int)key_index(dst[k - 1]);
       p.tau_score[q] = key_score(dst[k - 1]);
-      p.tau_idx[q] = key_index(dst[k - 1]);
+      p.tau_idx[q] = (uint32_t)(sample_block_row0(pos / kSampleBlockRows, nblk, sblk) + (pos % kSampleBlockRows));
     } else {
       p.tau_score[q] = -INFINITY;
       p.tau_idx[q] = 0xFFFFFFFFu;

@@ -129,7 +129,7 @@ def test_exact_ties_ascending_index(cuda_device):
 
 def _sampled_blocks(n):
     nblk = -(-n // 256)
-    sblk = max(74, int(0.02 * nblk + 0.5))
+    sblk = min(max(32, int(0.02 * nblk + 0.5)), 148)
     sblk = min(sblk, nblk - 1)
     return {(j * nblk) // sblk for j in range(sblk)}, nblk
 
