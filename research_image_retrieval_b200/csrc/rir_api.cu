@@ -189,6 +189,9 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     p.n = n_local; p.d = d; p.row_bytes = d * esz;
     p.nblk = pl.nblk; p.sblk = pl.sblk;
     p.sample_scores = reinterpret_cast<float*>(ws + pl.off_sample);
+    p.sample_keys = reinterpret_cast<unsigned long long*>(ws + pl.off_sample);
+    p.topt = 0;
+    p.sample_m = 0;
     p.tau_score = reinterpret_cast<float*>(ws + pl.off_tau_s);
     p.tau_idx = reinterpret_cast<uint32_t*>(ws + pl.off_tau_i);
     p.cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
@@ -222,6 +225,23 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
       if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
       p.mode = kModeScanAll;
     } else {
+      // what the sample pass keeps: best key per consumer warp (stream) / best T keys per sample tile (tcgen05);
+      // >= 2k kept keys per query keep tau tight; very large k falls back to the dense sample
+      const int sms = sm_count();
+      if (use_stream) {
+        if (2 * k <= sms * 8 && (size_t)sms * 8 * 8 <= (size_t)pl.sblk * kSampleBlockRows * 4) {
+          p.topt = 1;
+          p.sample_m = sms * 8;
+          RIR_CUDA_OK(cudaMemsetAsync(p.sample_keys, 0, (size_t)gq * p.sample_m * sizeof(unsigned long long), st));
+        }
+      } else {
+        int T = 1;
+        while (T < 8 && (long long)T * pl.sblk < 2ll * k) T <<= 1;
+        if ((long long)T * pl.sblk >= 2ll * k && (size_t)T * 8 <= (size_t)kSampleBlockRows * 4) {
+          p.topt = T;
+          p.sample_m = T * pl.sblk;
+        }
+      }
       if (int e = run_pass(kModeSample)) return e;
       if (int e = launch_sample_threshold(p, gq, k, st)) return e;
       RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (size_t)gq * sizeof(uint32_t), st));

@@ -5,9 +5,10 @@
 // without ever writing the [nq, n] score matrix to HBM.
 //
 // Scheme (exact):
-//   1. SAMPLE pass  : score `sblk` strided 256-row blocks of the shard densely -> sample_scores[nq, sblk*256].
-//   2. threshold    : tau[q] = k-th best (score, index) key of the sample.  The sample is a subset of the shard, so
-//                     tau[q] <= the true k-th best key: filtering with it can never drop a top-k row.
+//   1. SAMPLE pass  : score `sblk` strided 256-row blocks of the shard; keep, per query, the best few keys of every
+//                     CTA / warp (sample_keys) — or all sampled scores (sample_scores) when k is large.
+//   2. threshold    : tau[q] = k-th best (score, index) key among the kept ones.  They are scores of distinct rows
+//                     of the shard, so tau[q] <= the true k-th best key: filtering with it can never drop a top-k row.
 //   3. SCAN pass    : score every row once; rows whose key >= tau[q] are appended to cand[q, cap] (rare: ~k*n/S).
 //   4. final select : exact top-k of cand[q] (radix select + bitonic sort) -> out.
 //   5. fallback     : a query whose candidate list overflowed `cap` (adversarial row order) is re-done by the
@@ -34,7 +35,11 @@ struct SimParams {
   int mode;              // SimMode
   int nblk;              // ceil(n / 256)
   int sblk;              // sample blocks (<= nblk)
-  float* sample_scores;  // [nq_total, sblk*256]
+  float* sample_scores;  // [nq_total, sblk*256]   dense sample (topt == 0)
+  int topt;              // > 0: the sample pass keeps only the best `topt` keys per query per CTA (MMA path) or the best
+                         //      key per query per consumer warp (stream path) in sample_keys — enough to bound the k-th
+  int sample_m;          // slots per query in sample_keys (unwritten slots are 0 == "nothing")
+  unsigned long long* sample_keys;  // [nq_total, sample_m], aliases the sample_scores region
   float* tau_score;      // [nq_total]
   uint32_t* tau_idx;     // [nq_total]
   uint32_t* cnt;         // [nq_total] candidates appended per query (may exceed cap -> overflow)

@@ -37,7 +37,8 @@ constexpr int kABytes = kTileM * 128;  // 16 KB: 128 queries x 128 B of K
 constexpr int kBBytes = kTileN * 128;  // 32 KB: 256 database rows x 128 B of K
 constexpr int kMaxSlots = 8;
 constexpr int kTmemCols = 512;
-constexpr int kPend = 8;  // per-thread staged candidates before one atomicAdd reserves their slots
+constexpr int kPend = 8;
+constexpr int kMaxTopT = 8;  // per-thread staged candidates before one atomicAdd reserves their slots
 
 // Two independent TMA rings: the database ring is deep (its loads come from HBM: ~4 us loaded latency, so bytes in
 // flight decide the achieved bandwidth), the query ring is shallow when the kernel is HBM-bound (its chunks are L2
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
         npend = 0;
       }
     };
+    // sample mode with topt: this thread's (query's) best `topt` keys of the current sample tile
+    unsigned long long top[kMaxTopT];
     for (long long rd = 0; rd < g.rounds; ++rd) {
       long long t;
       int qb;
@@ -260,6 +263,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
         flush();
         pend_q = q;
       }
+#pragma unroll
+      for (int i = 0; i < kMaxTopT; ++i) top[i] = 0ull;
       float ts = INFINITY;
       uint32_t ti = 0;
       float qsc = 1.f;
@@ -311,7 +316,25 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
             }
           }
         } else if (qvalid) {
-          if (p.mode == kModeSample) {
+          if (p.mode == kModeSample && p.topt > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long row = row0 + c0 + j;
+              if (row < p.n) {
+                unsigned long long key = make_key(sc[j], (uint32_t)row);
+                if (key > top[kMaxTopT - 1] || p.topt < kMaxTopT) {
+#pragma unroll
+                  for (int i = 0; i < kMaxTopT; ++i) {  // insertion into the sorted (descending) top list
+                    if (i < p.topt && key > top[i]) {
+                      const unsigned long long tmp = top[i];
+                      top[i] = key;
+                      key = tmp;
+                    }
+                  }
+                }
+              }
+            }
+          } else if (p.mode == kModeSample) {
             float4* out = reinterpret_cast<float4*>(p.sample_scores + (size_t)q * sample_ld + (size_t)t * kTileN + c0);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -334,6 +357,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[ab]);
       if (++ab == 2) { ab = 0; aph ^= 1u; }
+      if (p.mode == kModeSample && p.topt > 0 && qvalid) {  // slot = (query, sample tile): every slot is written
+#pragma unroll
+        for (int i = 0; i < kMaxTopT; ++i)
+          if (i < p.topt) p.sample_keys[(size_t)q * p.sample_m + (size_t)t * p.topt + i] = top[i];
+      }
     }
     flush();
   }

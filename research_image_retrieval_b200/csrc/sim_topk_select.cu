@@ -19,6 +19,22 @@ __global__ void __launch_bounds__(kSelectThreads) sample_threshold_kernel(const 
   uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
   __shared__ SelectScratch sc;
   const int q = blockIdx.x;
+  if (p.topt > 0) {
+    // kept keys already carry their row index
+    const unsigned long long* kk = p.sample_keys + (size_t)q * p.sample_m;
+    auto key_at = [=](int i) -> unsigned long long { return kk[i]; };
+    const int got = block_select_topk(key_at, p.sample_m, k, dst, kpad, &sc);
+    if (threadIdx.x == 0) {
+      if (got >= k && dst[k - 1] != 0ull && key_score(dst[k - 1]) > -INFINITY) {
+        p.tau_score[q] = key_score(dst[k - 1]);
+        p.tau_idx[q] = key_index(dst[k - 1]);
+      } else {  // fewer than k kept keys: accept everything (the candidate list then overflows into the exact path)
+        p.tau_score[q] = -INFINITY;
+        p.tau_idx[q] = 0xFFFFFFFFu;
+      }
+    }
+    return;
+  }
   const int m = p.sblk * kSampleBlockRows;
   const float* s = p.sample_scores + (size_t)q * m;
   const int nblk = p.nblk, sblk = p.sblk;
@@ -65,11 +81,14 @@ __device__ __forceinline__ void write_sorted(const uint64_t* dst, int got, int k
   }
 }
 
+constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
+
 __global__ void __launch_bounds__(kSelectThreads)
     final_select_kernel(const SimParams p, int k, int kpad, long long idx_offset, float* out_score, int32_t* out_idx,
                         uint32_t* ovf) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
+  uint64_t* stage = dst + kpad;                            // [kStageKeys]
   __shared__ SelectScratch sc;
   const int q = blockIdx.x;
   const uint32_t cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : p.cnt[q];  // scan-all: slot == row
@@ -79,15 +98,24 @@ __global__ void __launch_bounds__(kSelectThreads)
   }
   if (threadIdx.x == 0) ovf[q] = 0u;
   const unsigned long long* c = p.cand + (size_t)q * p.cap;
-  auto key_at = [=](int i) -> unsigned long long { return c[i]; };
-  const int got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  int got;
+  if (cnt <= (uint32_t)kStageKeys && (int)cnt > k) {
+    for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) stage[i] = c[i];
+    __syncthreads();
+    const uint64_t* st = stage;
+    auto key_at = [=](int i) -> unsigned long long { return st[i]; };
+    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  } else {
+    auto key_at = [=](int i) -> unsigned long long { return c[i]; };
+    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  }
   write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
 }
 
 int launch_final_select(const SimParams& p, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
-  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t);
   RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   final_select_kernel<<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
   RIR_LAUNCH_OK();

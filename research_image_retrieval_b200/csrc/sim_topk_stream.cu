@@ -149,6 +149,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) sim_stream_kernel(const Sim
   const int chunks = p.row_bytes >> 4;
   int slot = 0;
   uint32_t phase = 0;
+  unsigned long long best[QB];  // sample mode with topt: this warp's best key per query (held by lane 0)
+#pragma unroll
+  for (int q = 0; q < QB; ++q) best[q] = 0ull;
   for (long long s = blockIdx.x; s < g.nstages_total; s += gridDim.x) {
     const long long row0 = stage_row0(s);
     mbar_wait(&full[slot], phase);
@@ -202,9 +205,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) sim_stream_kernel(const Sim
           if (q >= p.nq) continue;
           const float score = acc[r][q] * xs;
           if (p.mode == kModeSample) {
-            const long long pos = s * (long long)R + warp * RPW + r;  // dense position inside the sample
-            p.sample_scores[(size_t)(p.q0 + q) * ((size_t)p.sblk * kSampleBlockRows) + pos] =
-                valid ? score : -INFINITY;
+            if (p.topt > 0) {
+              if (valid) {
+                const unsigned long long key = make_key(score, (uint32_t)row);
+                best[q] = key > best[q] ? key : best[q];
+              }
+            } else {
+              const long long pos = s * (long long)R + warp * RPW + r;  // dense position inside the sample
+              p.sample_scores[(size_t)(p.q0 + q) * ((size_t)p.sblk * kSampleBlockRows) + pos] =
+                  valid ? score : -INFINITY;
+            }
           } else if (valid) {
             if (p.mode == kModeScanAll)  // slot == row (cap >= n): no atomics, the select kernel reads n entries
               p.cand[(size_t)(p.q0 + q) * p.cap + (size_t)row] = make_key(score, (uint32_t)row);
@@ -214,6 +224,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) sim_stream_kernel(const Sim
         }
       }
     }
+  }
+  if (p.mode == kModeSample && p.topt > 0 && lane == 0) {
+#pragma unroll
+    for (int q = 0; q < QB; ++q)
+      if (q < p.nq)
+        p.sample_keys[(size_t)(p.q0 + q) * p.sample_m + (size_t)blockIdx.x * kStreamConsumerWarps + warp] = best[q];
   }
 }
 
