@@ -50,6 +50,11 @@ int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
+  if (g_sm_count[dev] == 0) {  // workspace queries may come before the first launch
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_sm_count[dev] = n;
+    else cudaGetLastError();
+  }
   return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
 }
 
@@ -89,7 +94,7 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
     if (sblk > pl->nblk - 1) sblk = pl->nblk - 1;    // the last block may be partial: never sample it
     pl->sblk = (int)sblk;
     const double expected = (double)k * (double)n / ((double)sblk * kSampleBlockRows);
-    long long cap = pow2_ceil_int((int)(3.0 * expected) + 1024);
+    long long cap = pow2_ceil_int((int)(3.0 * expected) + 1024 + sm_count() * kFusedTopT);
     if (cap < 2048) cap = 2048;
     pl->cap = (int)cap;
   }
@@ -97,7 +102,7 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
   size_t o = 0;
   pl->off_tau_s = o; o = align_up(o + g * 4, 256);
   pl->off_tau_i = o; o = align_up(o + g * 4, 256);
-  pl->off_cnt = o;   o = align_up(o + g * 4, 256);
+  pl->off_cnt = o;   o = align_up(o + 2 * g * 4 + 64, 256);  // cnt | grid-barrier counters | tau flags (one memset)
   pl->off_ovf = o;   o = align_up(o + g * 4, 256);
   pl->off_sample = o; o = align_up(o + g * (size_t)pl->sblk * kSampleBlockRows * 4, 256);
   pl->off_cand = o;  o = align_up(o + g * (size_t)pl->cap * 8, 256);
@@ -198,7 +203,7 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     p.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
     p.cap = pl.cap;
     uint32_t* ovf = reinterpret_cast<uint32_t*>(ws + pl.off_ovf);
-    const bool use_stream = (path == RIR_PATH_STREAM) || dtype == RIR_F32 || (path == RIR_PATH_AUTO && gq <= 4);
+    const bool use_stream = (path == RIR_PATH_STREAM) || dtype == RIR_F32 || (path == RIR_PATH_AUTO && gq <= 2);
 
     auto run_pass = [&](int mode) -> int {
       p.mode = mode;
@@ -218,12 +223,22 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     };
 
     p.nq = gq;
+    p.k = k;
+    p.gbar = p.cnt + align_up((size_t)pl.group, 128);  // right behind cnt[]
+    p.tau_flag = p.gbar + 16;
     if (pl.scan_all) {
       // every row is a candidate: slot == row, cnt = n set by the select kernel's launch parameters
       if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
       if (int e = run_pass(kModeScanAll)) return e;
       if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
       p.mode = kModeScanAll;
+    } else if (!use_stream && mma_can_fuse(gq, n_local, k)) {
+      // ONE launch: the first round of the scan is the sample, tau is derived inside the kernel (sim_topk_mma.cu)
+      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (2 * align_up((size_t)pl.group, 128) + 16) * sizeof(uint32_t), st));
+      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
+      if (int e = run_pass(kModeFused)) return e;
+      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
+      p.mode = kModeFused;
     } else {
       // what the sample pass keeps: best key per consumer warp (stream) / best T keys per sample tile (tcgen05);
       // >= 2k kept keys per query keep tau tight; very large k falls back to the dense sample
@@ -252,7 +267,7 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     }
     float* os = out_score + (size_t)g0 * k;
     int32_t* oi = out_idx + (size_t)g0 * k;
-    if (int e = launch_final_select(p, gq, k, idx_offset, os, oi, ovf, st)) return e;
+    if (int e = launch_final_select(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
     if (!pl.scan_all) {
       // queries whose candidate list overflowed (adversarial row order) are redone exactly; no-op otherwise
       if (int e = launch_exact_scan(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;

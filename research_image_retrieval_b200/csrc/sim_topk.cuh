@@ -20,7 +20,8 @@ namespace rir {
 
 constexpr int kSampleBlockRows = 256;  // rows per sample block == MMA tile N
 
-enum SimMode : int { kModeScanFilter = 0, kModeSample = 1, kModeScanAll = 2 };
+enum SimMode : int { kModeScanFilter = 0, kModeSample = 1, kModeScanAll = 2, kModeFused = 3 };
+constexpr int kFusedTopT = 8;  // keys kept per (query, first-phase tile) in the fused scan
 
 struct SimParams {
   const void* Q;         // [nq, d]
@@ -45,6 +46,16 @@ struct SimParams {
   uint32_t* cnt;         // [nq_total] candidates appended per query (may exceed cap -> overflow)
   unsigned long long* cand;  // [nq_total, cap]
   int cap;
+  // fused scan (kModeFused, tcgen05 path): the first round(s) of the scan itself are the sample — each CTA keeps the
+  // best kFusedTopT keys per query of its first tile(s) in sample_keys, a grid barrier follows, tau is computed by the
+  // scan kernel and the remaining rounds filter with it.  Tiles are visited in a multiplicative permutation so the
+  // first `fused_tiles` of them are spread over the whole shard.
+  uint32_t* gbar;        // [2] grid-barrier counters (zeroed by the host before the launch)
+  uint32_t* tau_flag;    // [nq_total] set (release) once tau_score[q] is published (zeroed by the host)
+  int fused_tiles;       // first-phase tiles == slots per query in sample_keys / kFusedTopT
+  long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
+  long long perm_n;      // number of database tiles
+  int k;                 // top-k requested (the fused scan computes tau itself)
 };
 
 // first row of sample block j (strided over the whole shard so clustered / sorted databases are sampled fairly)
@@ -65,9 +76,12 @@ __device__ __forceinline__ bool passes(float score, uint32_t idx, float ts, uint
 
 // kernels' host launchers (defined in the .cu files)
 int launch_sim_stream(const SimParams& p, int dtype, cudaStream_t st);
-int launch_sim_mma(const SimParams& p, int dtype, cudaStream_t st);
+// fills p.topt / sample_m / fused_tiles / perm_* when p.mode == kModeFused
+int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st);
+// can the tcgen05 path run this problem as ONE fused launch (first-phase sample + in-kernel threshold)?
+bool mma_can_fuse(int nq, long long n, int k);
 int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st);
-int launch_final_select(const SimParams& p, int nq_total, int k, long long idx_offset, float* out_score,
+int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                       int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);

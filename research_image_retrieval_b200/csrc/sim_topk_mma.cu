@@ -5,44 +5,54 @@
 // adaptive_hybrid_retrieval_complete.py:428).  The [nq, n] score matrix lives only in TMEM.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0    TMA producer, database ring : cp.async.bulk.tensor 2-D tiles (256 rows x 128 B of K, 128B swizzle)
-//   warp 3    TMA producer, query ring    : 128 queries x 128 B of K (L2 resident)
-//   warp 1    MMA issuer   : one thread issues tcgen05.mma (M=128, N=256, K=16|32) — fp32 accumulators in TMEM,
-//                            double buffered (2 x 256 columns) so the epilogue overlaps the next tile
-//   warp 2    TMEM allocator
-//   warps 4-7 epilogue     : tcgen05.ld 32 lanes x 32 columns; thread == one query; running max against the
-//                            query's threshold tau; rare survivors are staged per thread and appended to the
-//                            candidate list with one atomicAdd per flush
-// Work item = (database tile, query block); items are tile-major so a database tile is pulled from HBM once and
-// re-read from L2 by the other query blocks.
+//   warp 0      TMA producer, database ring : cp.async.bulk.tensor 2-D tiles (256 rows x 128 B of K, 128B swizzle)
+//   warp 3      TMA producer, query ring    : MB x (<=128 queries x 128 B of K) (L2 resident)
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=256, K=16|32) — fp32 accumulators in TMEM
+//   warp 2      TMEM allocator
+//   warps 4..   epilogue (4 warps per query block): tcgen05.ld 32 lanes x 32 columns; thread == one query; running
+//               max against the query's threshold tau; rare survivors are staged per thread and appended to the
+//               candidate list with one atomicAdd per flush
+// Work item = (database tile, query super-block of MB x 128 queries).
+//   MB = 1 : two 256-column accumulators, the epilogue of one tile overlaps the MMAs of the next (HBM-bound batches)
+//   MB = 2 : two query blocks share every database chunk in shared memory (512 TMEM columns, one buffer).
+//            Measured on B200 this kernel is bound by the bytes DELIVERED INTO the SM (l1tex__m_xbar2l1tex_read_bytes
+//            ~8.6 TB/s chip-wide = ~32 B/clk/SM, multicast copies included), not by L2 or HBM: a 128x256 tile needs
+//            48 KB per 512 MMA clocks, a 256x256 tile 64 KB per 1024 — hence MB = 2 for tensor-bound batches, and
+//            the query box is trimmed to the real number of queries for single-block batches.
 //
-// Thread-block clusters (2 or 4 CTAs) cut the L2->SM traffic, which is what bounds this kernel once the epilogue
-// is cheap (measured: ~7.2 TB/s L2->SM on B200):
-//   one query block   : the CTAs of a cluster take DIFFERENT database tiles and SHARE the query chunk — each CTA
+// Thread-block clusters of 2 cut the L2 reads:
+//   one super-block   : the CTAs of a cluster take DIFFERENT database tiles and SHARE the query chunk — each CTA
 //                       loads 1/C of its rows and TMA-multicasts them to all C shared memories;
-//   several blocks    : the CTAs of a cluster take the SAME database tile and different query blocks — the
+//   several           : the CTAs of a cluster take the SAME database tile and different super-blocks — the
 //                       database chunk is the multicast operand.
 // A multicast slot may only be refilled once every CTA of the cluster has consumed it: the MMA warp's
 // tcgen05.commit for that ring is multicast to the `empty` barrier of all C CTAs (barrier count C).
+//
+// Fused mode (kModeFused): no separate sample / threshold launches.  The first `ra_rounds` rounds of the scan are
+// the sample: the epilogue keeps the best kFusedTopT keys per (query, tile) in sample_keys; a grid barrier follows
+// (all CTAs are co-resident: one per SM); every epilogue warp then derives tau for a few queries (3-pass radix over
+// the top 24 key bits: tau = lower edge of the bucket holding the k-th best kept key — still a lower bound of the
+// true k-th best, so the filter stays exact); a second grid barrier publishes tau and the remaining rounds filter.
+// The TMA / MMA warps keep running through the barriers (prefetching the next tile), so the bubble is hidden.
+// The first-phase keys are merged into the candidate list by final_select_kernel (sim_topk_select.cu).
 #include <cuda.h>
 #include <stdlib.h>
 #include "sim_topk.cuh"
 
 namespace rir {
 
-constexpr int kMmaThreads = 256;
 constexpr int kTileM = 128;  // queries per block (TMEM lanes)
 constexpr int kTileN = 256;  // database rows per tile (TMEM columns per accumulator)
 constexpr int kABytes = kTileM * 128;  // 16 KB: 128 queries x 128 B of K
 constexpr int kBBytes = kTileN * 128;  // 32 KB: 256 database rows x 128 B of K
 constexpr int kMaxSlots = 8;
 constexpr int kTmemCols = 512;
-constexpr int kPend = 8;
-constexpr int kMaxTopT = 8;  // per-thread staged candidates before one atomicAdd reserves their slots
+constexpr int kPend = 8;     // per-thread staged candidates before one atomicAdd reserves their slots
+constexpr int kMaxTopT = 8;  // keys kept per (query, sample tile)
+static_assert(kFusedTopT <= kMaxTopT, "fused sample keeps at most kMaxTopT keys");
 
 // Two independent TMA rings: the database ring is deep (its loads come from HBM: ~4 us loaded latency, so bytes in
-// flight decide the achieved bandwidth), the query ring is shallow when the kernel is HBM-bound (its chunks are L2
-// hits) and deeper when it is tensor-bound.
+// flight decide the achieved bandwidth), the query ring holds L2 hits.
 struct MmaSmemTail {
   uint64_t full_a[kMaxSlots], empty_a[kMaxSlots];
   uint64_t full_b[kMaxSlots], empty_b[kMaxSlots];
@@ -51,36 +61,46 @@ struct MmaSmemTail {
   uint32_t tmem_base;
   uint32_t pad;
   float xs[2][kTileN];
+  uint32_t hist[256];      // radix histogram of the fused threshold
+  uint32_t tau_prefix;     // radix-select state shared by the epilogue threads
+  uint32_t tau_need;
+  uint32_t tau_nz;
+  uint32_t pad2;
 };
 
 struct MmaGeom {
   int nqb;            // query blocks of 128
+  int nsb;            // query super-blocks of MB blocks
   long long ntiles;   // database tiles (scan) or sample blocks (sample mode)
   int kchunks;        // ceil(d / elements-per-128B)
   uint32_t idesc;     // tcgen05 instruction descriptor
   int x_streamed_once;
   int na, nb;         // ring depths (query chunks / database chunks)
-  int csize;          // cluster size: 1, 2 or 4
-  int share;          // 0 none, 1 query chunk shared (CTAs differ in tile), 2 database chunk shared (differ in query block)
-  int nqg;            // query-block groups = ceil(nqb / csize) when share == 2, else nqb
+  int csize;          // cluster size: 1 or 2
+  int share;          // 0 none, 1 query chunk shared (CTAs differ in tile), 2 database chunk shared (differ in super-block)
+  int nqg;            // super-block groups = ceil(nsb / csize) when share == 2, else nsb
   long long rounds;   // persistent-loop trips, identical for every CTA (dummy items keep clusters in lock step)
+  int a_rows;         // query rows per block actually loaded (multiple of 8 * sharers; 128 unless one small block)
+  int fused;          // kModeFused
+  int ra_rounds;      // fused: rounds [0, ra_rounds) are the sample phase
+  int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue math
 };
 
 enum { kShareNone = 0, kShareQ = 1, kShareX = 2 };
 
-// which (tile, query block) this CTA works on in round `rd`; tile may be >= ntiles (dummy item: all-OOB loads)
+// which (virtual tile, super-block) this CTA works on in round `rd`; v may be >= ntiles (dummy item: all-OOB loads)
 __device__ __forceinline__ void item_of(const MmaGeom& g, long long rd, int cluster_id, int nclusters, int crank,
-                                        long long* tile, int* qb) {
+                                        long long* v, int* sb) {
   const long long j = rd * nclusters + cluster_id;
   if (g.share == kShareQ) {
-    *tile = j * g.csize + crank;
-    *qb = 0;
+    *v = j * g.csize + crank;
+    *sb = 0;
   } else if (g.share == kShareX) {
-    *tile = j / g.nqg;
-    *qb = (int)(j % g.nqg) * g.csize + crank;
+    *v = j / g.nqg;
+    *sb = (int)(j % g.nqg) * g.csize + crank;
   } else {
-    *tile = j / g.nqb;
-    *qb = (int)(j % g.nqb);
+    *v = j / g.nsb;
+    *sb = (int)(j % g.nsb);
   }
 }
 
@@ -91,15 +111,129 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-template <int DT>
-__global__ void __launch_bounds__(kMmaThreads, 1)
+// one thread per CTA: arrive on a global counter and wait until all `expected` CTAs have (bounded: a bug must trap)
+__device__ __forceinline__ void grid_arrive_wait(uint32_t* ctr, uint32_t expected) {
+  __threadfence();
+  atomicAdd(ctr, 1u);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= expected) break;
+    __nanosleep(40);
+    if (clock64() - t0 > 8000000000ll) {
+      printf("librir: grid barrier timed out (block %d: %u of %u arrived)\n", (int)blockIdx.x, v, expected);
+      __trap();
+    }
+  }
+  __threadfence();
+}
+
+constexpr int kMaxFusedKeys = 1280;  // first-phase keys per query the in-kernel threshold can hold in registers
+
+// All epilogue threads (NE = 128 or 256): tau for query q = lower edge of the 24-bit bucket that holds the k-th best
+// kept key.  The keys are read once into registers; three 8-bit radix passes run on a shared-memory histogram.
+// Publishes tau_score[q] and then tau_flag[q] (release) — readers spin on the flag, there is no second grid barrier.
+template <int NE>
+__device__ __forceinline__ void cta_fused_tau(const SimParams& p, int q, int k, MmaSmemTail* tail, int etid) {
+  constexpr int KPT = kMaxFusedKeys / NE;
+  const unsigned long long* keys = p.sample_keys + (size_t)q * p.sample_m;
+  const int m = p.sample_m;
+  auto bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory"); };
+  unsigned long long kk[KPT];
+  int nz = 0;
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) {
+    const int idx = etid + i * NE;
+    kk[i] = idx < m ? __ldcg(keys + idx) : 0ull;
+    nz += kk[i] != 0ull ? 1 : 0;
+  }
+  for (int i = etid; i < 256; i += NE) tail->hist[i] = 0u;
+  if (etid == 0) tail->tau_nz = 0u;
+  bar();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+  if ((etid & 31) == 0 && nz) atomicAdd(&tail->tau_nz, (uint32_t)nz);
+  uint32_t prefix = 0u, need = (uint32_t)k;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 56 - 8 * pass;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      const unsigned long long key = kk[i];
+      if (key != 0ull && (pass == 0 || (uint32_t)(key >> (shift + 8)) == prefix))
+        atomicAdd(&tail->hist[(uint32_t)(key >> shift) & 255u], 1u);
+    }
+    bar();
+    if (etid < 32) {
+      // lane l owns digits [255-8l-7, 255-8l], walked from the top
+      uint32_t h[8];
+      uint32_t lane_sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        h[j] = tail->hist[255 - 8 * etid - j];
+        lane_sum += h[j];
+      }
+      uint32_t incl = lane_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (etid >= o) incl += v;
+      }
+      const uint32_t excl = incl - lane_sum;
+      if (excl < need && incl >= need) {  // at most one lane (none when fewer than `need` keys: handled via tau_nz)
+        uint32_t cum = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (cum < need && cum + h[j] >= need) {
+            tail->tau_prefix = (prefix << 8) | (255u - 8u * etid - j);
+            tail->tau_need = need - cum;
+          }
+          cum += h[j];
+        }
+      }
+    }
+    bar();
+    prefix = tail->tau_prefix;
+    need = tail->tau_need;
+    for (int i = etid; i < 256; i += NE) tail->hist[i] = 0u;
+    bar();
+  }
+  if (etid == 0) {
+    const float tau = tail->tau_nz >= (uint32_t)k ? ordered_to_float(prefix << 8) : -INFINITY;
+    p.tau_score[q] = tau;
+    p.tau_idx[q] = 0xFFFFFFFFu;  // every index passes at score == tau
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.tau_flag + q), "r"(1u) : "memory");
+  }
+}
+
+// value j (runtime) of a register array, by a select tree (no dynamic indexing -> no local memory)
+__device__ __forceinline__ float pick16(const float (&v)[16], int j) {
+  float a[8], b[4], c[2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = (j & 1) ? v[2 * t + 1] : v[2 * t];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) b[t] = (j & 2) ? a[2 * t + 1] : a[2 * t];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) c[t] = (j & 4) ? b[2 * t + 1] : b[2 * t];
+  return (j & 8) ? c[1] : c[0];
+}
+
+template <int DT, int MB>
+__global__ void __launch_bounds__(128 + 128 * MB, 1)
     sim_mma_kernel(const SimParams p, const MmaGeom g, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmX) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // layout: B ring [nb][32 KB] | A ring [na][16 KB] | tail
+  constexpr int kNumBuf = 2 / MB;             // TMEM accumulator buffers
+  constexpr int kBufCols = kTileN * MB;       // columns per buffer
+  constexpr int kASlot = kABytes * MB;        // query ring slot stride
+  constexpr int kEpiThreads = 128 * MB;
+  constexpr int kEpiWarps = 4 * MB;
+  // layout: B ring [nb][32 KB] | A ring [na][MB x 16 KB] | tail
   uint8_t* ring_b = smem;
   uint8_t* ring_a = smem + (size_t)g.nb * kBBytes;
-  MmaSmemTail* tail = reinterpret_cast<MmaSmemTail*>(ring_a + (size_t)g.na * kABytes);
+  MmaSmemTail* tail = reinterpret_cast<MmaSmemTail*>(ring_a + (size_t)g.na * kASlot);
   constexpr int kElemsPerChunk = (DT == RIR_BF16) ? 64 : 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +257,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->tmem_full[b], 1);
-      mbar_init(&tail->tmem_empty[b], 4);
+      mbar_init(&tail->tmem_empty[b], kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -141,9 +275,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
-  auto tile_row0 = [&](long long t) -> long long {  // dummy tiles (t >= ntiles) start past the last row
-    if (t >= g.ntiles) return ((p.n + kTileN - 1) / kTileN) * (long long)kTileN;
-    return p.mode == kModeSample ? sample_block_row0((int)t, p.nblk, p.sblk) : t * (long long)kTileN;
+  // virtual tile -> first database row.  Dummy tiles (v >= ntiles) start past the last row (all-OOB loads).
+  auto tile_row0 = [&](long long v) -> long long {
+    if (v >= g.ntiles) return ((p.n + kTileN - 1) / kTileN) * (long long)kTileN;
+    if (p.mode == kModeSample) return sample_block_row0((int)v, p.nblk, p.sblk);
+    if (g.fused) return ((v * p.perm_mul) % p.perm_n) * (long long)kTileN;
+    return v * (long long)kTileN;
   };
 
   if (warp == 0) {
@@ -156,10 +293,10 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
       uint32_t ph = 0;
       const int slice_rows = kTileN / cb, slice_bytes = kBBytes / cb;
       for (long long rd = 0; rd < g.rounds; ++rd) {
-        long long t;
-        int qb;
-        item_of(g, rd, cluster_id, nclusters, crank, &t, &qb);
-        const int row0 = (int)tile_row0(t);
+        long long v;
+        int sb;
+        item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
+        const int row0 = (int)tile_row0(v);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_b[s], ph ^ 1u);
           mbar_expect_tx(&tail->full_b[s], kBBytes);
@@ -180,20 +317,25 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_q));
       int s = 0;
       uint32_t ph = 0;
-      const int slice_rows = kTileM / ca, slice_bytes = kABytes / ca;
+      const int slice_rows = g.a_rows / ca, slice_bytes = slice_rows * 128;
+      const uint32_t tx_bytes = (uint32_t)(MB * g.a_rows * 128);
       for (long long rd = 0; rd < g.rounds; ++rd) {
-        long long t;
-        int qb;
-        item_of(g, rd, cluster_id, nclusters, crank, &t, &qb);
+        long long v;
+        int sb;
+        item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_a[s], ph ^ 1u);
-          mbar_expect_tx(&tail->full_a[s], kABytes);
-          uint8_t* dst = ring_a + (size_t)s * kABytes;
-          if (ca == 1)
-            tma_tensor2d_g2s(dst, &tmQ, kc * kElemsPerChunk, qb * kTileM, &tail->full_a[s], pol_q);
-          else
-            tma_tensor2d_g2s_mcast(dst + (size_t)crank * slice_bytes, &tmQ, kc * kElemsPerChunk,
-                                   qb * kTileM + crank * slice_rows, &tail->full_a[s], cmask, pol_q);
+          mbar_expect_tx(&tail->full_a[s], tx_bytes);
+#pragma unroll
+          for (int m = 0; m < MB; ++m) {
+            uint8_t* dst = ring_a + (size_t)s * kASlot + (size_t)m * kABytes;
+            const int qrow0 = (sb * MB + m) * kTileM;
+            if (ca == 1)
+              tma_tensor2d_g2s(dst, &tmQ, kc * kElemsPerChunk, qrow0, &tail->full_a[s], pol_q);
+            else
+              tma_tensor2d_g2s_mcast(dst + (size_t)crank * slice_bytes, &tmQ, kc * kElemsPerChunk,
+                                     qrow0 + crank * slice_rows, &tail->full_a[s], cmask, pol_q);
+          }
           if (++s == g.na) { s = 0; ph ^= 1u; }
         }
       }
@@ -201,42 +343,54 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int sa = 0, sb = 0;
+      int sa = 0, sb_ = 0;
       uint32_t pha = 0, phb = 0;
       int ab = 0;
       uint32_t aph = 0;
       for (long long rd = 0; rd < g.rounds; ++rd) {
         mbar_wait(&tail->tmem_empty[ab], aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kTileN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kBufCols);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->full_a[sa], pha);
-          mbar_wait(&tail->full_b[sb], phb);
+          mbar_wait(&tail->full_b[sb_], phb);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(smem_u32(ring_a + (size_t)sa * kABytes));
-          const uint64_t b_desc = make_smem_desc(smem_u32(ring_b + (size_t)sb * kBBytes));
+          const uint64_t b_desc = make_smem_desc(smem_u32(ring_b + (size_t)sb_ * kBBytes));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // advance 32 bytes of K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if (DT == RIR_BF16) umma_f16(d_tmem, a_desc + 2u * j, b_desc + 2u * j, g.idesc, (uint32_t)((kc | j) != 0));
-            else umma_f8(d_tmem, a_desc + 2u * j, b_desc + 2u * j, g.idesc, (uint32_t)((kc | j) != 0));
+          for (int m = 0; m < MB; ++m) {
+            if (g.debug & 1) break;
+            const uint64_t a_desc = make_smem_desc(smem_u32(ring_a + (size_t)sa * kASlot + (size_t)m * kABytes));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // advance 32 bytes of K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              if (DT == RIR_BF16)
+                umma_f16(d_tmem + (uint32_t)(m * kTileN), a_desc + 2u * j, b_desc + 2u * j, g.idesc,
+                         (uint32_t)((kc | j) != 0));
+              else
+                umma_f8(d_tmem + (uint32_t)(m * kTileN), a_desc + 2u * j, b_desc + 2u * j, g.idesc,
+                        (uint32_t)((kc | j) != 0));
+            }
           }
           // both slots are free once these MMAs have read them; a shared slot is released in every sharer
           if (ca == 1) umma_commit(&tail->empty_a[sa]); else umma_commit_mcast(&tail->empty_a[sa], cmask);
-          if (cb == 1) umma_commit(&tail->empty_b[sb]); else umma_commit_mcast(&tail->empty_b[sb], cmask);
+          if (cb == 1) umma_commit(&tail->empty_b[sb_]); else umma_commit_mcast(&tail->empty_b[sb_], cmask);
           if (++sa == g.na) { sa = 0; pha ^= 1u; }
-          if (++sb == g.nb) { sb = 0; phb ^= 1u; }
+          if (++sb_ == g.nb) { sb_ = 0; phb ^= 1u; }
         }
-        umma_commit(&tail->tmem_full[ab]);  // accumulator complete -> epilogue
-        if (++ab == 2) { ab = 0; aph ^= 1u; }
+        umma_commit(&tail->tmem_full[ab]);  // accumulators complete -> epilogue
+        if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: thread == query =====================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int ewi = warp - 4;      // epilogue warp index
+    const int mblk = ewi >> 2;     // query block inside the super-block
+    const int ew = ewi & 3;        // == warp % 4: the TMEM lane quarter this warp may read
+    const int etid = (int)threadIdx.x - 128;
     int ab = 0;
     uint32_t aph = 0;
     const size_t sample_ld = (size_t)p.sblk * kSampleBlockRows;
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
     // Survivors are staged per thread and their slots reserved with ONE atomicAdd per flush: the atomic's L2 round
     // trip (~1 us) must not be paid per candidate inside the tile loop (it was 96% of the kernel before).
     unsigned long long pend[kPend];
@@ -250,15 +404,31 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
         npend = 0;
       }
     };
-    // sample mode with topt: this thread's (query's) best `topt` keys of the current sample tile
+    // fused: publish the first-phase keys, then compute (and publish) tau for this CTA's share of the queries
+    auto fused_threshold = [&]() {
+      __threadfence();
+      epi_bar();
+      if (etid == 0) grid_arrive_wait(&p.gbar[0], gridDim.x);
+      epi_bar();
+      for (int q = (int)blockIdx.x; q < p.nq; q += (int)gridDim.x) cta_fused_tau<kEpiThreads>(p, q, p.k, tail, etid);
+    };
+    bool tau_ready = !g.fused;
+    const bool scaled = p.q_scale != nullptr || p.x_scale != nullptr;  // bf16 rows: scores are the raw accumulators
+    // sample / first phase: this thread's (query's) best `topt` keys of the current tile
     unsigned long long top[kMaxTopT];
     for (long long rd = 0; rd < g.rounds; ++rd) {
-      long long t;
-      int qb;
-      item_of(g, rd, cluster_id, nclusters, crank, &t, &qb);
-      const long long row0 = tile_row0(t);
-      const int q = qb * kTileM + ew * 32 + lane;
-      const bool qvalid = q < p.nq && t < g.ntiles;
+      if (g.fused && rd == g.ra_rounds) {
+        flush();
+        fused_threshold();
+        tau_ready = true;
+      }
+      const int mode = g.fused ? (rd < g.ra_rounds ? (int)kModeSample : (int)kModeScanFilter) : p.mode;
+      long long v;
+      int sb;
+      item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
+      const long long row0 = tile_row0(v);
+      const int q = (sb * MB + mblk) * kTileM + ew * 32 + lane;
+      const bool qvalid = q < p.nq && v < g.ntiles;
       if (q != pend_q) {
         flush();
         pend_q = q;
@@ -269,75 +439,109 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
       uint32_t ti = 0;
       float qsc = 1.f;
       if (qvalid) {
-        if (p.mode == kModeScanFilter) {
-          ts = p.tau_score[q];
-          ti = p.tau_idx[q];
-        }
-        if (p.q_scale) qsc = p.q_scale[q];
-      }
-      if (p.x_scale) {  // stage this tile's row scales (uniform branch)
-        const int e = ew * 32 + lane;
-        for (int j = e; j < kTileN; j += 128) {
-          const long long row = row0 + j;
-          tail->xs[ab][j] = row < p.n ? p.x_scale[row] : 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      mbar_wait(&tail->tmem_full[ab], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * kTileN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < kTileN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        float sc[32];
-        if (p.x_scale) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]) * qsc * tail->xs[ab][c0 + j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]) * qsc;
-        }
-        if (p.mode == kModeScanFilter) {
-          float mx = sc[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sc[j]);
-          if (mx >= ts) {  // rare: ~k*n/S survivors per query over the whole scan
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (sc[j] >= ts) {
-                const long long row = row0 + c0 + j;
-                if (row < p.n && passes(sc[j], (uint32_t)row, ts, ti)) {
-                  if (npend == kPend) flush();
-                  pend[npend++] = make_key(sc[j], (uint32_t)row);
-                }
+        if (mode == kModeScanFilter) {
+          if (g.fused) {  // tau[q] is published by whichever CTA computed it
+            const long long t0 = clock64();
+            while (true) {
+              uint32_t f;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.tau_flag + q) : "memory");
+              if (f != 0u) break;
+              __nanosleep(40);
+              if (clock64() - t0 > 8000000000ll) {
+                printf("librir: fused threshold of query %d never arrived (block %d)\n", q, (int)blockIdx.x);
+                __trap();
               }
             }
           }
+          ts = __ldcg(&p.tau_score[q]);
+          ti = __ldcg(&p.tau_idx[q]);
+        }
+        if (p.q_scale) qsc = p.q_scale[q];
+      }
+      // the barrier below lets a warp run at most one round ahead of the slowest: two buffers, by round parity
+      const int xb = (int)(rd & 1);
+      if (p.x_scale) {  // stage this tile's row scales (uniform branch)
+        for (int j = etid; j < kTileN; j += kEpiThreads) {
+          const long long row = row0 + j;
+          tail->xs[xb][j] = row < p.n ? p.x_scale[row] : 0.f;
+        }
+        epi_bar();
+      }
+      const long long dbg_t0 = (g.debug & 4) ? clock64() : 0;
+      mbar_wait(&tail->tmem_full[ab], aph);
+      tc_fence_after();
+      const long long dbg_t1 = (g.debug & 4) ? clock64() : 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * kBufCols + mblk * kTileN);
+      // 16 columns at a time, double buffered: the tcgen05.ld of the next unit is in flight while this one is
+      // processed (TMEM loads take a few hundred clocks while the MMAs of the other accumulator are running).
+      // Survivors are found with a per-lane bitmask — no divergent per-column branches (the unrolled 32-way version
+      // of this code took ~27k clocks per tile, 10x the budget) — and each lane then walks ITS bits, fetching the
+      // score from registers with a select tree, so the score array is never indexed dynamically.
+      auto process16 = [&](const uint32_t (&vv)[16], int c0) {
+        float sc[16];
+        if (p.x_scale) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]) * qsc * tail->xs[xb][c0 + j];
+        } else if (scaled) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]) * qsc;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]);
+        }
+        if (mode == kModeScanFilter) {
+          uint32_t mask = 0u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mask |= (sc[j] >= ts) ? (1u << j) : 0u;
+          // qvalid: lanes of queries that do not exist hold whatever the (trimmed) query box left in shared memory
+          if (!qvalid) mask = 0u;
+#pragma unroll 1
+          while (mask) {  // rare: ~k*n/S survivors per query over the whole scan
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float s1 = pick16(sc, j);
+            const long long row = row0 + c0 + j;
+            if (row < p.n && passes(s1, (uint32_t)row, ts, ti)) {
+              if (npend == kPend) flush();
+              pend[npend++] = make_key(s1, (uint32_t)row);
+            }
+          }
         } else if (qvalid) {
-          if (p.mode == kModeSample && p.topt > 0) {
+          if (mode == kModeSample && p.topt > 0) {
+            // columns that can enter this lane's running top list: score >= its current last kept score
+            unsigned long long last = top[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int i = 1; i < kMaxTopT; ++i)
+              if (i < p.topt) last = top[i];
+            const float thr = last != 0ull ? key_score(last) : -INFINITY;
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mask |= (sc[j] >= thr) ? (1u << j) : 0u;
+#pragma unroll 1
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1u;
               const long long row = row0 + c0 + j;
-              if (row < p.n) {
-                unsigned long long key = make_key(sc[j], (uint32_t)row);
-                if (key > top[kMaxTopT - 1] || p.topt < kMaxTopT) {
+              unsigned long long key = make_key(pick16(sc, j), (uint32_t)row);
+              if (row < p.n && key > last) {
 #pragma unroll
-                  for (int i = 0; i < kMaxTopT; ++i) {  // insertion into the sorted (descending) top list
-                    if (i < p.topt && key > top[i]) {
-                      const unsigned long long tmp = top[i];
-                      top[i] = key;
-                      key = tmp;
-                    }
+                for (int i = 0; i < kMaxTopT; ++i) {  // insertion into the sorted (descending) top list
+                  if (i < p.topt && key > top[i]) {
+                    const unsigned long long tmp = top[i];
+                    top[i] = key;
+                    key = tmp;
                   }
                 }
+                last = top[0];
+#pragma unroll
+                for (int i = 1; i < kMaxTopT; ++i)
+                  if (i < p.topt) last = top[i];
               }
             }
-          } else if (p.mode == kModeSample) {
-            float4* out = reinterpret_cast<float4*>(p.sample_scores + (size_t)q * sample_ld + (size_t)t * kTileN + c0);
+          } else if (mode == kModeSample) {
+            float4* out = reinterpret_cast<float4*>(p.sample_scores + (size_t)q * sample_ld + (size_t)v * kTileN + c0);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 16; j += 4) {
               float4 o;
               o.x = (row0 + c0 + j + 0 < p.n) ? sc[j + 0] : -INFINITY;
               o.y = (row0 + c0 + j + 1 < p.n) ? sc[j + 1] : -INFINITY;
@@ -348,22 +552,39 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
           } else {  // kModeScanAll: slot == row (cap >= n), no atomics
             unsigned long long* out = p.cand + (size_t)q * p.cap + (size_t)(row0 + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (row0 + c0 + j < p.n) out[j] = make_key(sc[j], (uint32_t)(row0 + c0 + j));
           }
+        }
+      };
+      if (!(g.debug & 2)) {
+        uint32_t va[16], vb[16];
+        tmem_ld_32x32_x16(taddr, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTileN; c0 += 32) {
+          tmem_ld_wait();
+          tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 16), vb);
+          process16(va, c0);
+          tmem_ld_wait();
+          if (c0 + 32 < kTileN) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
+          process16(vb, c0 + 16);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[ab]);
-      if (++ab == 2) { ab = 0; aph ^= 1u; }
-      if (p.mode == kModeSample && p.topt > 0 && qvalid) {  // slot = (query, sample tile): every slot is written
+      if ((g.debug & 4) && blockIdx.x < 2 && lane == 0 && rd < 6)
+        printf("dbg cta %d warp %d rd %lld: wait %lld clk, columns %lld clk\n", (int)blockIdx.x, warp, rd,
+               dbg_t1 - dbg_t0, clock64() - dbg_t1);
+      if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
+      if (mode == kModeSample && p.topt > 0 && qvalid) {  // slot = (query, sample tile): every slot is written
 #pragma unroll
         for (int i = 0; i < kMaxTopT; ++i)
-          if (i < p.topt) p.sample_keys[(size_t)q * p.sample_m + (size_t)t * p.topt + i] = top[i];
+          if (i < p.topt) p.sample_keys[(size_t)q * p.sample_m + (size_t)v * p.topt + i] = top[i];
       }
     }
     flush();
+    if (!tau_ready) fused_threshold();
   }
 
   tc_fence_before();
@@ -416,66 +637,44 @@ static int make_rowmajor_map(CUtensorMap* m, const void* base, long long rows, i
   return RIR_OK;
 }
 
-int launch_sim_mma(const SimParams& p, int dtype, cudaStream_t st) {
-  if (dtype != RIR_BF16 && dtype != RIR_FP8E4M3) {
-    set_error("sim_topk(mma): unsupported dtype %d", dtype);
-    return RIR_E_ARG;
-  }
-  if (p.n >= (1ll << 31) - kTileN) {
-    set_error("sim_topk(mma): shard too large (%lld rows)", p.n);
-    return RIR_E_ARG;
-  }
-  MmaGeom g;
-  g.nqb = (p.nq + kTileM - 1) / kTileM;
-  g.ntiles = p.mode == kModeSample ? p.sblk : (p.n + kTileN - 1) / kTileN;
-  const int epc = dtype == RIR_BF16 ? 64 : 128;
-  g.kchunks = (p.d + epc - 1) / epc;
-  const uint32_t fmt = dtype == RIR_BF16 ? 1u : 0u;  // F16F32Format::BF16 = 1 ; MXF8F6F4Format::E4M3 = 0
-  g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-            ((uint32_t)(kTileM >> 4) << 24);
-  g.x_streamed_once = (g.nqb == 1);
-  // ring depths: measured on B200 (70 queries, 1M x 2048 bf16) 4+4 >= 3+5 >= 2+6 within 3% — the kernel is bound by
-  // bytes delivered to the SMs (~6.7 TB/s for HBM fills + L2 hits together), not by bytes in flight
-  g.na = 4;
-  g.nb = 4;
-  // clusters: share the query chunk across tiles (one block) or the database chunk across query blocks (several)
-  const int sms = sm_count();
-  // pairs only: clusters of 4 cannot be placed on 16 of the 148 SMs (GPC sizes 16/18/20), which costs a second wave
-  g.csize = (sms % 2 == 0) ? 2 : 1;
-  g.share = g.csize == 1 ? kShareNone : (g.nqb == 1 ? kShareQ : kShareX);
-  if (const char* e = getenv("RIR_MMA_RINGS")) {  // tuning override "na,nb" (development only)
-    int a = 0, b = 0;
-    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a <= kMaxSlots && b <= kMaxSlots &&
-        (size_t)b * kBBytes + (size_t)a * kABytes + sizeof(MmaSmemTail) <= 227 * 1024) {
-      g.na = a;
-      g.nb = b;
-    }
-  }
-  if (const char* e = getenv("RIR_MMA_CLUSTER")) {  // tuning override: cluster size 1 / 2 / 4 (development only)
-    const int c = atoi(e);
-    if ((c == 1 || c == 2 || c == 4) && sms % c == 0) {
-      g.csize = c;
-      g.share = c == 1 ? kShareNone : (g.nqb == 1 ? kShareQ : kShareX);
-    }
-  }
-  g.nqg = g.share == kShareX ? (g.nqb + g.csize - 1) / g.csize : g.nqb;
-  long long cluster_items;
-  if (g.share == kShareQ) cluster_items = (g.ntiles + g.csize - 1) / g.csize;
-  else if (g.share == kShareX) cluster_items = g.ntiles * g.nqg;
-  else cluster_items = g.ntiles * g.nqb;
-  if (cluster_items <= 0) return RIR_OK;
-  long long nclusters = sms / g.csize;
-  if (nclusters > cluster_items) nclusters = cluster_items;
-  g.rounds = (cluster_items + nclusters - 1) / nclusters;
-  const int ca = g.share == kShareQ ? g.csize : 1, cb = g.share == kShareX ? g.csize : 1;
-  CUtensorMap tmQ, tmX;
-  if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, kTileM / ca)) return e;
-  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, kTileN / cb)) return e;
-  const size_t smem_bytes = (size_t)g.nb * kBBytes + (size_t)g.na * kABytes + sizeof(MmaSmemTail);
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
+static int cluster_size_for(int sms) {
+  // pairs only: clusters of 4 cannot be placed on 16 of the 148 SMs (GPC sizes 16/18/20), which costs a second wave
+  int c = (sms % 2 == 0) ? 2 : 1;
+  const int o = env_int("RIR_MMA_CLUSTER", 0);  // tuning override (development only)
+  if ((o == 1 || o == 2) && sms % o == 0) c = o;
+  return c;
+}
+
+static long long gcd_ll(long long a, long long b) {
+  while (b) {
+    const long long t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+bool mma_can_fuse(int nq, long long n, int k) {
+  (void)nq;
+  if (env_int("RIR_MMA_FUSED", 1) == 0) return false;
+  const int sms = sm_count();
+  const long long ntiles = (n + kTileN - 1) / kTileN;
+  // the first phase (one tile per CTA and query) must hold >= 2k keys and be a small part of the scan
+  return (long long)sms * kFusedTopT >= 2ll * k && sms * kFusedTopT <= kMaxFusedKeys && ntiles >= 2ll * sms;
+}
+
+template <int DT, int MB>
+static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
+                        unsigned grid, cudaStream_t st) {
+  const size_t smem_bytes = (size_t)g.nb * kBBytes + (size_t)g.na * kABytes * MB + sizeof(MmaSmemTail);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(nclusters * g.csize));
-  cfg.blockDim = dim3(kMmaThreads);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(128 + 128 * MB);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -485,17 +684,96 @@ int launch_sim_mma(const SimParams& p, int dtype, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (dtype == RIR_BF16) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
-    RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<RIR_BF16>, p, g, tmQ, tmX));
-  } else {
-    RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
-    RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<RIR_FP8E4M3>, p, g, tmQ, tmX));
-  }
+  RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<DT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB>, p, g, tmQ, tmX));
   RIR_LAUNCH_OK();
   return RIR_OK;
+}
+
+int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
+  if (dtype != RIR_BF16 && dtype != RIR_FP8E4M3) {
+    set_error("sim_topk(mma): unsupported dtype %d", dtype);
+    return RIR_E_ARG;
+  }
+  if (p.n >= (1ll << 31) - kTileN) {
+    set_error("sim_topk(mma): shard too large (%lld rows)", p.n);
+    return RIR_E_ARG;
+  }
+  const int sms = sm_count();
+  MmaGeom g;
+  g.nqb = (p.nq + kTileM - 1) / kTileM;
+  int mb = g.nqb >= 2 ? 2 : 1;
+  {
+    const int o = env_int("RIR_MMA_MB", 0);  // tuning override (development only)
+    if (o == 1 || o == 2) mb = o;
+  }
+  g.nsb = (g.nqb + mb - 1) / mb;
+  g.ntiles = p.mode == kModeSample ? p.sblk : (p.n + kTileN - 1) / kTileN;
+  const int epc = dtype == RIR_BF16 ? 64 : 128;
+  g.kchunks = (p.d + epc - 1) / epc;
+  const uint32_t fmt = dtype == RIR_BF16 ? 1u : 0u;  // F16F32Format::BF16 = 1 ; MXF8F6F4Format::E4M3 = 0
+  g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+            ((uint32_t)(kTileM >> 4) << 24);
+  g.x_streamed_once = (g.nsb == 1);
+  // ring depths: ~192 KB of shared memory either way
+  g.na = mb == 1 ? 4 : 3;
+  g.nb = mb == 1 ? 4 : 3;
+  g.csize = cluster_size_for(sms);
+  g.share = g.csize == 1 ? kShareNone : (g.nsb == 1 ? kShareQ : kShareX);
+  if (const char* e = getenv("RIR_MMA_RINGS")) {  // tuning override "na,nb" (development only)
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a <= kMaxSlots && b <= kMaxSlots &&
+        (size_t)b * kBBytes + (size_t)a * kABytes * mb + sizeof(MmaSmemTail) <= 227 * 1024) {
+      g.na = a;
+      g.nb = b;
+    }
+  }
+  const int ca = g.share == kShareQ ? g.csize : 1, cb = g.share == kShareX ? g.csize : 1;
+  // one small query block: load only the rows that exist (multiple of 8 rows per sharer: 1024-byte swizzle atoms)
+  g.a_rows = kTileM;
+  if (g.nqb == 1 && mb == 1 && env_int("RIR_MMA_TRIM", 1) != 0) {
+    const int unit = 8 * ca;
+    g.a_rows = (p.nq + unit - 1) / unit * unit;
+    if (g.a_rows > kTileM) g.a_rows = kTileM;
+  }
+  g.nqg = g.share == kShareX ? (g.nsb + g.csize - 1) / g.csize : g.nsb;
+  long long cluster_items;
+  if (g.share == kShareQ) cluster_items = (g.ntiles + g.csize - 1) / g.csize;
+  else if (g.share == kShareX) cluster_items = g.ntiles * g.nqg;
+  else cluster_items = g.ntiles * g.nsb;
+  if (cluster_items <= 0) return RIR_OK;
+  long long nclusters = sms / g.csize;
+  if (nclusters > cluster_items) nclusters = cluster_items;
+  g.rounds = (cluster_items + nclusters - 1) / nclusters;
+  const unsigned grid = (unsigned)(nclusters * g.csize);
+
+  g.debug = env_int("RIR_MMA_DEBUG", 0);
+  g.fused = p.mode == kModeFused ? 1 : 0;
+  g.ra_rounds = 0;
+  if (g.fused) {
+    // first phase: every (query, tile v < grid) pair — one tile per CTA and query
+    if ((int)grid != sms || g.ntiles < 2ll * grid) {
+      set_error("sim_topk(mma): fused scan needs a full grid (internal error: mma_can_fuse not honoured)");
+      return RIR_E_ARG;
+    }
+    g.ra_rounds = g.share == kShareQ ? 1 : (g.share == kShareX ? g.nqg * g.csize : g.nsb);
+    p.topt = kFusedTopT;
+    p.fused_tiles = (int)grid;
+    p.sample_m = (int)grid * kFusedTopT;
+    p.perm_n = g.ntiles;
+    long long mul = g.ntiles / grid;  // consecutive virtual tiles land ~ntiles/grid apart
+    if (mul < 1) mul = 1;
+    while (gcd_ll(mul, g.ntiles) != 1) ++mul;
+    if (env_int("RIR_MMA_PERM", 1) == 0) mul = 1;  // tuning override (development only)
+    p.perm_mul = mul;
+  }
+  CUtensorMap tmQ, tmX;
+  if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, g.a_rows / ca)) return e;
+  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, kTileN / cb)) return e;
+  if (dtype == RIR_BF16)
+    return mb == 1 ? launch_mma_t<RIR_BF16, 1>(p, g, tmQ, tmX, grid, st) : launch_mma_t<RIR_BF16, 2>(p, g, tmQ, tmX, grid, st);
+  return mb == 1 ? launch_mma_t<RIR_FP8E4M3, 1>(p, g, tmQ, tmX, grid, st)
+                 : launch_mma_t<RIR_FP8E4M3, 2>(p, g, tmQ, tmX, grid, st);
 }
 
 }  // namespace rir

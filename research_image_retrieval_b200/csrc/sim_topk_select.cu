@@ -65,70 +65,8 @@ int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_
 }
 
 // ---------------------------------------------------------------------------------------------
-// final: exact top-k of each query's candidate list
+// CUDA-core dot products (fallback / redo / rescore paths): one warp per row, fp32 FMA
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void write_sorted(const uint64_t* dst, int got, int k, long long idx_offset,
-                                             float* out_score, int32_t* out_idx) {
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const uint64_t key = dst[i];
-    if (i < got && key != 0ull) {
-      out_score[i] = key_score(key);
-      out_idx[i] = (int32_t)((long long)key_index(key) + idx_offset);
-    } else {
-      out_score[i] = -INFINITY;
-      out_idx[i] = -1;
-    }
-  }
-}
-
-constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
-
-__global__ void __launch_bounds__(kSelectThreads)
-    final_select_kernel(const SimParams p, int k, int kpad, long long idx_offset, float* out_score, int32_t* out_idx,
-                        uint32_t* ovf) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
-  uint64_t* stage = dst + kpad;                            // [kStageKeys]
-  __shared__ SelectScratch sc;
-  const int q = blockIdx.x;
-  const uint32_t cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : p.cnt[q];  // scan-all: slot == row
-  if (cnt > (uint32_t)p.cap) {  // candidate list overflowed: the exact fallback kernel owns this query
-    if (threadIdx.x == 0) ovf[q] = 1u;
-    return;
-  }
-  if (threadIdx.x == 0) ovf[q] = 0u;
-  const unsigned long long* c = p.cand + (size_t)q * p.cap;
-  int got;
-  if (cnt <= (uint32_t)kStageKeys && (int)cnt > k) {
-    for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) stage[i] = c[i];
-    __syncthreads();
-    const uint64_t* st = stage;
-    auto key_at = [=](int i) -> unsigned long long { return st[i]; };
-    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
-  } else {
-    auto key_at = [=](int i) -> unsigned long long { return c[i]; };
-    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
-  }
-  write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
-}
-
-int launch_final_select(const SimParams& p, int nq_total, int k, long long idx_offset, float* out_score,
-                        int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
-  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
-  const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t);
-  RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  final_select_kernel<<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
-  RIR_LAUNCH_OK();
-  return RIR_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// robust exact scan: one CTA per query, running top-k in shared memory.  Used (a) for queries whose candidate
-// list overflowed, (b) as RIR_PATH_EXACT — an independent second implementation for the parity tests.
-// ---------------------------------------------------------------------------------------------
-constexpr int kExactThreads = 256;
-constexpr int kExactRowsPerIter = 32;  // 8 warps x 4 rows
-
 template <int DT>
 __device__ __forceinline__ float dot_row(const uint8_t* row, const float* qs, int chunks, int lane);
 
@@ -182,6 +120,171 @@ __device__ __forceinline__ float dot_row<RIR_FP8E4M3>(const uint8_t* row, const 
   }
   return warp_sum(acc);
 }
+
+
+// query row q -> fp32 shared memory (q_scale folded in)
+template <int DT>
+__device__ __forceinline__ void load_query_f32(const SimParams& p, int q, float* qs) {
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) {
+    float v;
+    if (DT == RIR_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.Q)[(size_t)q * p.d + i]);
+    else if (DT == RIR_F32) v = reinterpret_cast<const float*>(p.Q)[(size_t)q * p.d + i];
+    else {
+      const __half_raw h =
+          __nv_cvt_fp8_to_halfraw(reinterpret_cast<const __nv_fp8_storage_t*>(p.Q)[(size_t)q * p.d + i], __NV_E4M3);
+      v = __half2float(*reinterpret_cast<const __half*>(&h));
+    }
+    if (p.q_scale) v *= p.q_scale[q];
+    qs[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// final: exact top-k of each query's candidate list
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_sorted(const uint64_t* dst, int got, int k, long long idx_offset,
+                                             float* out_score, int32_t* out_idx) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const uint64_t key = dst[i];
+    if (i < got && key != 0ull) {
+      out_score[i] = key_score(key);
+      out_idx[i] = (int32_t)((long long)key_index(key) + idx_offset);
+    } else {
+      out_score[i] = -INFINITY;
+      out_idx[i] = -1;
+    }
+  }
+}
+
+constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
+constexpr int kMaxRedo = 64;      // first-phase tiles per query that may need a re-score before the exact path takes over
+
+// Fused scan: the first-phase tiles left only their best kFusedTopT keys per query (sample_keys).  Keys >= tau join
+// the candidate list here.  A tile whose LAST kept key still passes tau may hold more passing rows than were kept:
+// it is re-scored with CUDA-core dot products (rare: P[>= 8 of 256 rows above the ~k/148-per-tile rate]).
+template <int DT>
+__device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uint32_t* cnt_io, float* qs,
+                                                  uint32_t* s_extra, int* s_nredo, int* s_redo) {
+  const float ts = p.tau_score[q];
+  const unsigned long long* keys = p.sample_keys + (size_t)q * p.sample_m;
+  unsigned long long* c = p.cand + (size_t)q * p.cap;
+  const uint32_t cnt = *cnt_io;
+  const int T = p.topt, slots = p.fused_tiles;
+  if (threadIdx.x == 0) {
+    *s_extra = 0u;
+    *s_nredo = 0;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < slots; s += blockDim.x) {
+    const unsigned long long last = keys[(size_t)s * T + T - 1];
+    if (last != 0ull && key_score(last) >= ts) {
+      const int i = atomicAdd(s_nredo, 1);
+      if (i < kMaxRedo) s_redo[i] = s;
+    } else {
+      for (int i = 0; i < T; ++i) {
+        const unsigned long long key = keys[(size_t)s * T + i];
+        if (key != 0ull && key_score(key) >= ts) {
+          const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
+          if (pos < (uint32_t)p.cap) c[pos] = key;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int nredo = *s_nredo;
+  if (nredo > kMaxRedo) return false;  // hand the query to the exact path
+  if (nredo > 0) {
+    load_query_f32<DT>(p, q, qs);
+    __syncthreads();
+    // the re-score uses fp32 FMAs, the scan used the tensor core: accept with a margin, the select sorts it out
+    const float ts_lo = ts - 1e-4f * (fabsf(ts) + 1e-2f);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int chunks = p.row_bytes >> 4;
+    for (int r = 0; r < nredo; ++r) {
+      const long long tile = ((long long)s_redo[r] * p.perm_mul) % p.perm_n;
+      const long long row0 = tile * kSampleBlockRows;
+      for (long long row = row0 + warp; row < row0 + kSampleBlockRows && row < p.n; row += nwarps) {
+        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
+        if (p.x_scale) s *= p.x_scale[row];
+        if (lane == 0 && s >= ts_lo) {
+          const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
+          if (pos < (uint32_t)p.cap) c[pos] = make_key(s, (uint32_t)row);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  *cnt_io = cnt + *s_extra;
+  return true;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kSelectThreads)
+    final_select_kernel(const SimParams p, int k, int kpad, long long idx_offset, float* out_score, int32_t* out_idx,
+                        uint32_t* ovf) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
+  uint64_t* stage = dst + kpad;                            // [kStageKeys]
+  float* qs = reinterpret_cast<float*>(stage + kStageKeys);  // [d] (fused mode only)
+  __shared__ SelectScratch sc;
+  __shared__ uint32_t s_extra;
+  __shared__ int s_nredo;
+  __shared__ int s_redo[kMaxRedo];
+  const int q = blockIdx.x;
+  uint32_t cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : p.cnt[q];  // scan-all: slot == row
+  bool ok = cnt <= (uint32_t)p.cap;
+  if (ok && p.mode == kModeFused) {
+    ok = merge_first_phase<DT>(p, q, &cnt, qs, &s_extra, &s_nredo, s_redo);
+    ok = ok && cnt <= (uint32_t)p.cap;
+  }
+  if (!ok) {  // candidate list overflowed: the exact fallback kernel owns this query
+    if (threadIdx.x == 0) ovf[q] = 1u;
+    return;
+  }
+  if (threadIdx.x == 0) ovf[q] = 0u;
+  const unsigned long long* c = p.cand + (size_t)q * p.cap;
+  int got;
+  if (cnt <= (uint32_t)kStageKeys && (int)cnt > k) {
+    for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) stage[i] = c[i];
+    __syncthreads();
+    const uint64_t* st = stage;
+    auto key_at = [=](int i) -> unsigned long long { return st[i]; };
+    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  } else {
+    auto key_at = [=](int i) -> unsigned long long { return c[i]; };
+    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+  }
+  write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+}
+
+int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
+                        int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t) + (p.mode == kModeFused ? (size_t)p.d * sizeof(float) : 0);
+  if (smem > 220 * 1024) {
+    set_error("sim_topk(select): k=%d d=%d needs %zu B of shared memory", k, p.d, smem);
+    return RIR_E_ARG;
+  }
+  if (dtype == RIR_BF16) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_select_kernel<RIR_BF16><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+  } else if (dtype == RIR_FP8E4M3) {
+    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_select_kernel<RIR_FP8E4M3><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+  } else {
+    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_select_kernel<RIR_F32><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+  }
+  RIR_LAUNCH_OK();
+  return RIR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// robust exact scan: one CTA per query, running top-k in shared memory.  Used (a) for queries whose candidate
+// list overflowed, (b) as RIR_PATH_EXACT — an independent second implementation for the parity tests.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExactThreads = 256;
+constexpr int kExactRowsPerIter = 32;  // 8 warps x 4 rows
 
 template <int DT>
 __global__ void __launch_bounds__(kExactThreads)

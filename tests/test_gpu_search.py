@@ -77,6 +77,52 @@ def test_sim_topk_paths(cuda_device, dtype, path, nq, n, d, k):
             assert set(planted[r].tolist()) <= set(got[r, : max(k, planted.shape[1])].tolist())
 
 
+FUSED_CASES = [
+    # nq, n, d, k, dtype   (n >= 2 * 148 * 256 rows: the tcgen05 path runs as ONE fused launch)
+    (70, 100003, 256, 100, "bf16"),   # one query block, query box trimmed to 80 rows, pair shares the query chunk
+    (5, 90000, 128, 10, "bf16"),      # tiny batch on the tensor path (box trimmed to 16 rows)
+    (130, 80000, 64, 50, "fp8"),      # two query blocks in one CTA (512 TMEM columns)
+    (300, 90000, 128, 100, "bf16"),   # two super-blocks: pair shares the database chunk, one dummy query block
+    (600, 76000, 64, 20, "bf16"),     # three super-blocks (odd): dummy super-block in the last pair
+]
+
+
+@pytest.mark.parametrize("nq,n,d,k,dtype", FUSED_CASES)
+def test_fused_scan(cuda_device, nq, n, d, k, dtype):
+    """Fused tcgen05 scan (first round = sample, in-kernel threshold, grid barrier) vs the oracle."""
+    Q, X, planted = synth.retrieval_set(nq, n, d, seed=n + nq)
+    db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k, path="mma")
+    torch.cuda.synchronize()
+    Xf = _dequant(db.rows, db.scale, dtype)[:, :d]
+    Qf = _dequant(qr, qs, dtype)[:, :d]
+    _check(sc, ix, Qf, Xf, k, 1e-3)
+    # the exact path is an independent implementation: same indices up to ties
+    sc2, ix2 = db.search(qr[:4].contiguous(), None if qs is None else qs[:4].contiguous(), k, path="exact")
+    ok, msg = S.indices_match_up_to_ties(ix[:4].cpu().numpy().astype(np.int64), sc[:4].cpu().numpy(),
+                                         ix2.cpu().numpy().astype(np.int64), sc2.cpu().numpy(), 1e-3)
+    assert ok, msg
+
+
+def test_fused_scan_first_phase_redo(cuda_device):
+    """Clustered database: tile 0 (always a first-phase tile) holds 40 near-duplicates of query 0 — more than the 8 keys
+    the first phase keeps per tile — so the select kernel must re-score that tile.  Another 30 sit in the last tile."""
+    nq, n, d, k = 6, 120000, 128, 64
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=4242, n_pos=0)
+    gen = torch.Generator().manual_seed(6)
+    near = Q[0][None, :] + torch.randn(70, d, generator=gen) * (0.3 / d ** 0.5)
+    near = near / near.norm(dim=1, keepdim=True)
+    rows = np.concatenate([np.arange(3, 43), np.arange(n - 30, n)])
+    X[torch.from_numpy(rows)] = near
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k, path="mma")
+    Xf, Qf = db.rows.float().cpu(), qr.float().cpu()
+    _check(sc, ix, Qf, Xf, k, 1e-3)
+    assert set(ix[0].cpu().tolist()) <= set(rows.tolist())
+
+
 def test_fp8_against_fp32_rescore(cuda_device):
     """fp8 bar (north_star): indices exact except ties within 5e-3 relative, judged on TRUE fp32 scores.  The fp8 scan
     over-fetches 2k+16 candidates and a bf16 re-score of those rows decides the final order."""
