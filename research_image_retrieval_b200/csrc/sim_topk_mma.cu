@@ -220,7 +220,7 @@ __device__ __forceinline__ float pick16(const float (&v)[16], int j) {
   return (j & 8) ? c[1] : c[0];
 }
 
-template <int DT, int MB>
+template <int DT, int MB, int TWO>
 __global__ void __launch_bounds__(128 + 128 * MB, 1)
     sim_mma_kernel(const SimParams p, const MmaGeom g, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmX) {
@@ -228,11 +228,12 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   constexpr int kNumBuf = 2 / MB;             // TMEM accumulator buffers
   constexpr int kBufCols = kTileN * MB;       // columns per buffer
   constexpr int kASlot = kABytes * MB;        // query ring slot stride
+  constexpr int kBSlot = TWO ? kBBytes / 2 : kBBytes;  // CTA pair: each CTA holds its 128 of the tile's 256 rows
   constexpr int kEpiThreads = 128 * MB;
   constexpr int kEpiWarps = 4 * MB;
   // layout: B ring [nb][32 KB] | A ring [na][MB x 16 KB] | tail
   uint8_t* ring_b = smem;
-  uint8_t* ring_a = smem + (size_t)g.nb * kBBytes;
+  uint8_t* ring_a = smem + (size_t)g.nb * kBSlot;
   MmaSmemTail* tail = reinterpret_cast<MmaSmemTail*>(ring_a + (size_t)g.na * kASlot);
   constexpr int kElemsPerChunk = (DT == RIR_BF16) ? 64 : 128;
 
@@ -241,8 +242,11 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   const int cluster_id = blockIdx.x / g.csize;
   const int nclusters = gridDim.x / g.csize;
   const uint16_t cmask = (uint16_t)((1u << g.csize) - 1u);
-  const int ca = g.share == kShareQ ? g.csize : 1;  // CTAs sharing one query chunk
-  const int cb = g.share == kShareX ? g.csize : 1;  // CTAs sharing one database chunk
+  const int ca = (!TWO && g.share == kShareQ) ? g.csize : 1;  // CTAs sharing one query chunk (multicast)
+  const int cb = (!TWO && g.share == kShareX) ? g.csize : 1;  // CTAs sharing one database chunk (multicast)
+  // CTA pair (TWO): the leader (cluster rank 0) issues every MMA for both SMs; both CTAs' TMA loads complete on the
+  // LEADER's full barriers; tcgen05.commit releases ring slots / publishes accumulators in both CTAs.
+  const bool leader = !TWO || crank == 0;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {  // SWIZZLE_128B tiles need 1024-byte aligned shared memory
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->tmem_full[b], 1);
-      mbar_init(&tail->tmem_empty[b], kEpiWarps);
+      mbar_init(&tail->tmem_empty[b], TWO ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues free the leader
     }
     mbar_fence_init();
   }
@@ -266,8 +270,13 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     tma_prefetch_desc(&tmX);
   }
   if (warp == 2) {
-    tmem_alloc(&tail->tmem_base, kTmemCols);
-    tmem_relinquish();
+    if (TWO) {
+      tmem_alloc_2sm(&tail->tmem_base, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(&tail->tmem_base, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -299,13 +308,19 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         const int row0 = (int)tile_row0(v);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_b[s], ph ^ 1u);
-          mbar_expect_tx(&tail->full_b[s], kBBytes);
-          uint8_t* dst = ring_b + (size_t)s * kBBytes;
-          if (cb == 1)
-            tma_tensor2d_g2s(dst, &tmX, kc * kElemsPerChunk, row0, &tail->full_b[s], pol_x);
-          else  // my 1/cb of the rows, delivered to every CTA of the cluster
-            tma_tensor2d_g2s_mcast(dst + (size_t)crank * slice_bytes, &tmX, kc * kElemsPerChunk,
-                                   row0 + crank * slice_rows, &tail->full_b[s], cmask, pol_x);
+          uint8_t* dst = ring_b + (size_t)s * kBSlot;
+          if (TWO) {  // my 128 rows into my shared memory; both halves complete on the leader's barrier
+            if (leader) mbar_expect_tx(&tail->full_b[s], kBBytes);
+            tma_tensor2d_g2s_2sm(dst, &tmX, kc * kElemsPerChunk, row0 + crank * (kTileN / 2),
+                                 mapa_u32(smem_u32(&tail->full_b[s]), 0), pol_x);
+          } else {
+            mbar_expect_tx(&tail->full_b[s], kBBytes);
+            if (cb == 1)
+              tma_tensor2d_g2s(dst, &tmX, kc * kElemsPerChunk, row0, &tail->full_b[s], pol_x);
+            else  // my 1/cb of the rows, delivered to every CTA of the cluster
+              tma_tensor2d_g2s_mcast(dst + (size_t)crank * slice_bytes, &tmX, kc * kElemsPerChunk,
+                                     row0 + crank * slice_rows, &tail->full_b[s], cmask, pol_x);
+          }
           if (++s == g.nb) { s = 0; ph ^= 1u; }
         }
       }
@@ -325,12 +340,19 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_a[s], ph ^ 1u);
-          mbar_expect_tx(&tail->full_a[s], tx_bytes);
+          if (TWO) {
+            if (leader) mbar_expect_tx(&tail->full_a[s], 2u * tx_bytes);
+          } else {
+            mbar_expect_tx(&tail->full_a[s], tx_bytes);
+          }
 #pragma unroll
           for (int m = 0; m < MB; ++m) {
             uint8_t* dst = ring_a + (size_t)s * kASlot + (size_t)m * kABytes;
             const int qrow0 = (sb * MB + m) * kTileM;
-            if (ca == 1)
+            if (TWO)
+              tma_tensor2d_g2s_2sm(dst, &tmQ, kc * kElemsPerChunk, qrow0, mapa_u32(smem_u32(&tail->full_a[s]), 0),
+                                   pol_q);
+            else if (ca == 1)
               tma_tensor2d_g2s(dst, &tmQ, kc * kElemsPerChunk, qrow0, &tail->full_a[s], pol_q);
             else
               tma_tensor2d_g2s_mcast(dst + (size_t)crank * slice_bytes, &tmQ, kc * kElemsPerChunk,
@@ -341,8 +363,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (CTA pair: the leader only) =====================
+    if (lane == 0 && leader) {
       int sa = 0, sb_ = 0;
       uint32_t pha = 0, phb = 0;
       int ab = 0;
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           mbar_wait(&tail->full_a[sa], pha);
           mbar_wait(&tail->full_b[sb_], phb);
           tc_fence_after();
-          const uint64_t b_desc = make_smem_desc(smem_u32(ring_b + (size_t)sb_ * kBBytes));
+          const uint64_t b_desc = make_smem_desc(smem_u32(ring_b + (size_t)sb_ * kBSlot));
 #pragma unroll
           for (int m = 0; m < MB; ++m) {
             if (g.debug & 1) break;
@@ -363,21 +385,30 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               // advance 32 bytes of K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              if (DT == RIR_BF16)
-                umma_f16(d_tmem + (uint32_t)(m * kTileN), a_desc + 2u * j, b_desc + 2u * j, g.idesc,
-                         (uint32_t)((kc | j) != 0));
-              else
-                umma_f8(d_tmem + (uint32_t)(m * kTileN), a_desc + 2u * j, b_desc + 2u * j, g.idesc,
-                        (uint32_t)((kc | j) != 0));
+              const uint32_t dcol = d_tmem + (uint32_t)(m * kTileN);
+              const uint32_t acc = (uint32_t)((kc | j) != 0);
+              if (TWO) {
+                if (DT == RIR_BF16) umma_f16_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+                else umma_f8_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+              } else {
+                if (DT == RIR_BF16) umma_f16(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+                else umma_f8(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+              }
             }
           }
           // both slots are free once these MMAs have read them; a shared slot is released in every sharer
-          if (ca == 1) umma_commit(&tail->empty_a[sa]); else umma_commit_mcast(&tail->empty_a[sa], cmask);
-          if (cb == 1) umma_commit(&tail->empty_b[sb_]); else umma_commit_mcast(&tail->empty_b[sb_], cmask);
+          if (TWO) {
+            umma_commit_2sm(&tail->empty_a[sa], cmask);
+            umma_commit_2sm(&tail->empty_b[sb_], cmask);
+          } else {
+            if (ca == 1) umma_commit(&tail->empty_a[sa]); else umma_commit_mcast(&tail->empty_a[sa], cmask);
+            if (cb == 1) umma_commit(&tail->empty_b[sb_]); else umma_commit_mcast(&tail->empty_b[sb_], cmask);
+          }
           if (++sa == g.na) { sa = 0; pha ^= 1u; }
           if (++sb_ == g.nb) { sb_ = 0; phb ^= 1u; }
         }
-        umma_commit(&tail->tmem_full[ab]);  // accumulators complete -> epilogue
+        // accumulators complete -> epilogue (of both CTAs of a pair)
+        if (TWO) umma_commit_2sm(&tail->tmem_full[ab], cmask); else umma_commit(&tail->tmem_full[ab]);
         if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
       }
     }
@@ -393,16 +424,33 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
     // Survivors are staged per thread and their slots reserved with ONE atomicAdd per flush: the atomic's L2 round
     // trip (~1 us) must not be paid per candidate inside the tile loop (it was 96% of the kernel before).
-    unsigned long long pend[kPend];
-    int npend = 0;
-    int pend_q = 0;
-    auto flush = [&]() {
-      if (npend > 0) {
-        const uint32_t base = atomicAdd(&p.cnt[pend_q], (uint32_t)npend);
-        for (int i = 0; i < npend; ++i)
-          if (base + (uint32_t)i < (uint32_t)p.cap) p.cand[(size_t)pend_q * p.cap + base + i] = pend[i];
-        npend = 0;
-      }
+    // The reservation is also DEFERRED: the atomic is issued when a staging buffer fills, its result is first used
+    // when the other buffer fills (or at the end of the query's rounds), so its latency overlaps the tile loop.
+    unsigned long long pend[2][kPend];
+    int npend = 0;       // entries in pend[cur]
+    int cur = 0;
+    int out_n = 0;       // entries of pend[cur ^ 1] whose slots are reserved (query out_q, base out_base), not yet written
+    uint32_t out_base = 0;
+    int out_q = 0;
+    int pend_q = 0;      // query of the entries in pend[cur]
+    auto drain = [&]() {  // write the reserved batch
+      for (int i = 0; i < out_n; ++i)
+        if (out_base + (uint32_t)i < (uint32_t)p.cap) p.cand[(size_t)out_q * p.cap + out_base + i] = pend[cur ^ 1][i];
+      out_n = 0;
+    };
+    // staging buffer full, or the thread moves on to another query: reserve slots for it and switch buffers.  The
+    // batch reserved LAST time is written first — a tile ago, so that atomic has long returned.
+    auto reserve = [&]() {
+      drain();
+      out_base = atomicAdd(&p.cnt[pend_q], (uint32_t)npend);
+      out_n = npend;
+      out_q = pend_q;
+      cur ^= 1;
+      npend = 0;
+    };
+    auto flush = [&]() {  // everything out (end of the scan / before the grid barrier)
+      if (npend > 0) reserve();
+      drain();
     };
     // fused: publish the first-phase keys, then compute (and publish) tau for this CTA's share of the queries
     auto fused_threshold = [&]() {
@@ -411,6 +459,23 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       if (etid == 0) grid_arrive_wait(&p.gbar[0], gridDim.x);
       epi_bar();
       for (int q = (int)blockIdx.x; q < p.nq; q += (int)gridDim.x) cta_fused_tau<kEpiThreads>(p, q, p.k, tail, etid);
+      // every tau this CTA will read is published by some CTA's loop above: wait for all flags once (no acquire /
+      // L1 invalidate per round later), then one fence
+      for (int q = etid; q < p.nq; q += kEpiThreads) {
+        const long long t0 = clock64();
+        while (true) {
+          uint32_t f;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.tau_flag + q) : "memory");
+          if (f != 0u) break;
+          __nanosleep(40);
+          if (clock64() - t0 > 8000000000ll) {
+            printf("librir: fused threshold of query %d never arrived (block %d)\n", q, (int)blockIdx.x);
+            __trap();
+          }
+        }
+      }
+      __threadfence();
+      epi_bar();
     };
     bool tau_ready = !g.fused;
     const bool scaled = p.q_scale != nullptr || p.x_scale != nullptr;  // bf16 rows: scores are the raw accumulators
@@ -430,7 +495,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       const int q = (sb * MB + mblk) * kTileM + ew * 32 + lane;
       const bool qvalid = q < p.nq && v < g.ntiles;
       if (q != pend_q) {
-        flush();
+        if (npend > 0) reserve();
         pend_q = q;
       }
 #pragma unroll
@@ -440,19 +505,6 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       float qsc = 1.f;
       if (qvalid) {
         if (mode == kModeScanFilter) {
-          if (g.fused) {  // tau[q] is published by whichever CTA computed it
-            const long long t0 = clock64();
-            while (true) {
-              uint32_t f;
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.tau_flag + q) : "memory");
-              if (f != 0u) break;
-              __nanosleep(40);
-              if (clock64() - t0 > 8000000000ll) {
-                printf("librir: fused threshold of query %d never arrived (block %d)\n", q, (int)blockIdx.x);
-                __trap();
-              }
-            }
-          }
           ts = __ldcg(&p.tau_score[q]);
           ti = __ldcg(&p.tau_idx[q]);
         }
@@ -460,6 +512,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       }
       // the barrier below lets a warp run at most one round ahead of the slowest: two buffers, by round parity
       const int xb = (int)(rd & 1);
+      const __nv_bfloat162 ts2 = __float2bfloat162_rn(ts);
       if (p.x_scale) {  // stage this tile's row scales (uniform branch)
         for (int j = etid; j < kTileN; j += kEpiThreads) {
           const long long row = row0 + j;
@@ -477,7 +530,13 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       // Survivors are found with a per-lane bitmask — no divergent per-column branches (the unrolled 32-way version
       // of this code took ~27k clocks per tile, 10x the budget) — and each lane then walks ITS bits, fetching the
       // score from registers with a select tree, so the score array is never indexed dynamically.
+      uint32_t dbg_acc = 0u;
       auto process16 = [&](const uint32_t (&vv)[16], int c0) {
+        if (g.debug & 8) {  // development: TMEM loads only
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dbg_acc ^= vv[j];
+          return;
+        }
         float sc[16];
         if (p.x_scale) {
 #pragma unroll
@@ -490,20 +549,26 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]);
         }
         if (mode == kModeScanFilter) {
+          // pre-filter on packed bf16 pairs (3 instructions per 2 columns): round-to-nearest is monotonic, so
+          // score >= ts implies bf16(score) >= bf16(ts) — it can only let extra columns through, which the exact fp32
+          // test below rejects.  bit j = column 2j, bit 16+j = column 2j+1.
           uint32_t mask = 0u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mask |= (sc[j] >= ts) ? (1u << j) : 0u;
+          for (int j = 0; j < 8; ++j)
+            mask |= __hge2_mask(__floats2bfloat162_rn(sc[2 * j], sc[2 * j + 1]), ts2) & (0x00010001u << j);
           // qvalid: lanes of queries that do not exist hold whatever the (trimmed) query box left in shared memory
           if (!qvalid) mask = 0u;
+          if (g.debug & 16) mask &= (mask == 0x12345678u) ? ~0u : 0u;  // development: no slow path
 #pragma unroll 1
           while (mask) {  // rare: ~k*n/S survivors per query over the whole scan
-            const int j = __ffs(mask) - 1;
+            const int b = __ffs(mask) - 1;
             mask &= mask - 1u;
+            const int j = ((b & 15) << 1) | (b >> 4);
             const float s1 = pick16(sc, j);
             const long long row = row0 + c0 + j;
             if (row < p.n && passes(s1, (uint32_t)row, ts, ti)) {
-              if (npend == kPend) flush();
-              pend[npend++] = make_key(s1, (uint32_t)row);
+              if (npend == kPend) reserve();
+              pend[cur][npend++] = make_key(s1, (uint32_t)row);
             }
           }
         } else if (qvalid) {
@@ -572,7 +637,11 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->tmem_empty[ab]);
+      if (lane == 0) {
+        if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[ab]), 0));  // the leader's MMA thread waits
+        else mbar_arrive(&tail->tmem_empty[ab]);
+      }
+      if ((g.debug & 8) && dbg_acc == 0x9e3779b9u) p.tau_idx[0] = dbg_acc;  // keeps the loads alive
       if ((g.debug & 4) && blockIdx.x < 2 && lane == 0 && rd < 6)
         printf("dbg cta %d warp %d rd %lld: wait %lld clk, columns %lld clk\n", (int)blockIdx.x, warp, rd,
                dbg_t1 - dbg_t0, clock64() - dbg_t1);
@@ -592,7 +661,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   if (g.csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (TWO) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -668,10 +737,11 @@ bool mma_can_fuse(int nq, long long n, int k) {
   return (long long)sms * kFusedTopT >= 2ll * k && sms * kFusedTopT <= kMaxFusedKeys && ntiles >= 2ll * sms;
 }
 
-template <int DT, int MB>
+template <int DT, int MB, int TWO>
 static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
                         unsigned grid, cudaStream_t st) {
-  const size_t smem_bytes = (size_t)g.nb * kBBytes + (size_t)g.na * kABytes * MB + sizeof(MmaSmemTail);
+  const size_t smem_bytes =
+      (size_t)g.nb * (TWO ? kBBytes / 2 : kBBytes) + (size_t)g.na * kABytes * MB + sizeof(MmaSmemTail);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(128 + 128 * MB);
@@ -684,10 +754,18 @@ static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<DT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB>, p, g, tmQ, tmX));
+  RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<DT, MB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem_bytes));
+  RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB, TWO>, p, g, tmQ, tmX));
   RIR_LAUNCH_OK();
   return RIR_OK;
+}
+
+template <int DT>
+static int launch_mma_d(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
+                        unsigned grid, int mb, int two, cudaStream_t st) {
+  if (two) return mb == 1 ? launch_mma_t<DT, 1, 1>(p, g, tmQ, tmX, grid, st) : launch_mma_t<DT, 2, 1>(p, g, tmQ, tmX, grid, st);
+  return mb == 1 ? launch_mma_t<DT, 1, 0>(p, g, tmQ, tmX, grid, st) : launch_mma_t<DT, 2, 0>(p, g, tmQ, tmX, grid, st);
 }
 
 int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
@@ -702,7 +780,9 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   const int sms = sm_count();
   MmaGeom g;
   g.nqb = (p.nq + kTileM - 1) / kTileM;
-  int mb = g.nqb >= 2 ? 2 : 1;
+  // Measured on B200 (1M x 2048 bf16): CTA pair + one block per CTA (epilogue overlapped with the next tile's MMAs)
+  // 1220 TFLOP/s at 1024 queries; pair + two blocks per CTA 1110 (its epilogue is not overlapped); no pair 1074-1107.
+  int mb = 1;
   {
     const int o = env_int("RIR_MMA_MB", 0);  // tuning override (development only)
     if (o == 1 || o == 2) mb = o;
@@ -728,7 +808,14 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
       g.nb = b;
     }
   }
-  const int ca = g.share == kShareQ ? g.csize : 1, cb = g.share == kShareX ? g.csize : 1;
+  // CTA pair (cta_group::2): the two CTAs of a cluster work on the same database tile and different super-blocks;
+  // one M=256 MMA spans both SMs, each CTA stages only its 128 of the tile's 256 rows (no multicast needed)
+  const int two = (g.share == kShareX && env_int("RIR_MMA_TWO", 1) != 0) ? 1 : 0;
+  if (two) {
+    g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    g.na = g.nb = mb == 1 ? 6 : 4;
+  }
+  const int ca = (!two && g.share == kShareQ) ? g.csize : 1, cb = two ? 2 : (g.share == kShareX ? g.csize : 1);
   // one small query block: load only the rows that exist (multiple of 8 rows per sharer: 1024-byte swizzle atoms)
   g.a_rows = kTileM;
   if (g.nqb == 1 && mb == 1 && env_int("RIR_MMA_TRIM", 1) != 0) {
@@ -770,10 +857,8 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   CUtensorMap tmQ, tmX;
   if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, g.a_rows / ca)) return e;
   if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, kTileN / cb)) return e;
-  if (dtype == RIR_BF16)
-    return mb == 1 ? launch_mma_t<RIR_BF16, 1>(p, g, tmQ, tmX, grid, st) : launch_mma_t<RIR_BF16, 2>(p, g, tmQ, tmX, grid, st);
-  return mb == 1 ? launch_mma_t<RIR_FP8E4M3, 1>(p, g, tmQ, tmX, grid, st)
-                 : launch_mma_t<RIR_FP8E4M3, 2>(p, g, tmQ, tmX, grid, st);
+  if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, grid, mb, two, st);
+  return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, grid, mb, two, st);
 }
 
 }  // namespace rir
