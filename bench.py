@@ -292,30 +292,51 @@ def run_ours(args):
     value = args.nq * args.steps / (ms * 1e-3)
     e2e_value = args.nq * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (the full scan): algorithmic bytes / measured launch duration ----
-    alg_bytes = n_local * args.d * esz + args.nq * args.d * esz + 0
+    # ---- roofline of the dominant kernel (the scan): algorithmic work / measured launch duration ----
+    # HBM-bound while 2*nq flop per database byte stays under the ridge (~214 flop/B, i.e. nq < ~200 for bf16),
+    # tensor-bound above.
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     except Exception:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (scan_avg_ms * 1e-3) / 1e9
+    stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2)
+    kernel_name = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("sim_scan_dram_bytes_per_launch")
+            traffic = json.load(f).get("sim_scan_dram_bytes_per_launch" if not stream_path else
+                                       "sim_stream_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "kernel": "sim_mma_kernel (scan pass)" if (args.path == "mma" or (args.path == "auto" and args.nq > 4)) else "sim_stream_kernel (scan pass)",
-                "kernel_ms": scan_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+    flops = 2.0 * args.nq * n_local * args.d
+    alg_bytes = n_local * args.d * esz + args.nq * args.d * esz
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    if flops / alg_bytes < 214.0:
+        achieved = alg_bytes / (scan_avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "kernel": kernel_name, "kernel_ms": scan_avg_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"}
+    else:
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0)) * (2.0 if args.dtype == "fp8" else 1.0)
+        achieved = flops / (scan_avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                    "traffic": traffic, "kernel": kernel_name, "kernel_ms": scan_avg_ms,
+                    "algorithmic_flops_per_launch": flops,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone (of measured)" if peaks
+                                    else "1590 TFLOP/s (of fallback, B200_PROFILING.md)") +
+                                   (" x2 for fp8" if args.dtype == "fp8" else "")}
 
-    kernels_per_step = 5 + (1 if world > 1 else 0)  # sample, threshold, scan, select, overflow-fallback [, merge]
-    if args.n // world <= 16384:
-        kernels_per_step = 2 + (1 if world > 1 else 0)
+    # our kernels per step: fused tcgen05 path = scan, select, overflow fallback; stream path adds sample + threshold
+    if n_local <= 16384:
+        kernels_per_step = 2
+    elif stream_path:
+        kernels_per_step = 5
+    else:
+        kernels_per_step = 3
+    kernels_per_step += 1 if world > 1 else 0  # merge
 
     if rank == 0:
         line = {

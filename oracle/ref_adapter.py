@@ -13,6 +13,12 @@ import warnings
 
 REF_ROOT = os.environ.get("RIR_REFERENCE_ROOT", "/root/reference")
 REF_BENCH = os.path.join(REF_ROOT, "src", "benchmark")
+# The unmodified reference also installs offline (pip --no-deps --target baseline/_ref); that copy is
+# git-ignored but travels to the GPU box, so the oracle can be checked against the real reference there too.
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "benchmark")
+if not os.path.isfile(os.path.join(REF_BENCH, "utils", "evaluate.py")) and os.path.isfile(
+        os.path.join(_INSTALLED, "utils", "evaluate.py")):
+    REF_ROOT, REF_BENCH = os.path.dirname(_INSTALLED), _INSTALLED
 
 
 def available() -> bool:
