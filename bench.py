@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"])
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     return ap.parse_args()
 
 
@@ -227,6 +228,13 @@ def run_ours(args):
             scales.append(s)
         db = rir.Database(torch.cat(parts), torch.cat(scales), "fp8", idx_offset=lo)
     sdb = rir.ShardedDatabase(db)
+    exchange = "none (1 GPU)"
+    if world > 1:
+        # the one exchange step of the sharded search: NVLink peer-memory stores from the select kernel + a waiting
+        # merge kernel (rir_sim_topk_sharded); --exchange nccl keeps the all-gather + merge path
+        exchange = "nccl all-gather + merge kernel"
+        if args.exchange == "peer" and sdb.enable_peer_exchange(args.nq, args.k):
+            exchange = "nvlink peer-memory stores + waiting merge kernel (no collective call)"
     q_host = make_queries_fp32(args.nq, args.d).pin_memory()
     qr, qs = db.pack_queries(q_host.to(dev))
     k = args.k
@@ -301,7 +309,7 @@ def run_ours(args):
             peaks = json.load(f)
     except Exception:
         pass
-    stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2)
+    stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2 and n_local < 2 * 148 * 256)
     kernel_name = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
     traffic = None
     try:
@@ -342,7 +350,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, {"path": args.path}),
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, {"path": args.path, "exchange": exchange}),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.nq * args.d * 4,
                     "d2h_bytes_per_step": args.nq * k * 8, "ms_per_step": ms_e2e / args.steps,
@@ -363,6 +371,7 @@ def run_ours(args):
             }
         print(json.dumps(line))
     if world > 1:
+        sdb.close()
         dist.destroy_process_group()
 
 

@@ -141,6 +141,29 @@ size_t rir_merge_topk_workspace(int G, int nq, int k);
 int rir_merge_topk(const float* sc, const int32_t* ix, int G, int nq, int k, float* out_sc, int32_t* out_ix,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Sharded search over NVLink peer memory (one process per GPU; no reference counterpart)
+ *
+ * Every rank owns an inbox of rir_exchange_bytes(G, nq_max, k_max) bytes that all peers map with CUDA IPC.
+ * rir_sim_topk_sharded = rir_sim_topk on the local shard whose select kernel STORES the local top-k into slot `rank`
+ * of every rank's inbox (P2P stores + a release flag per query), followed by a merge kernel that waits for the G
+ * flags of each query and merges the G lists: out_score / out_idx [nq,k] hold the GLOBAL top-k on every rank.  There
+ * is no collective-library call on the data path.  Semantics of a collective: every rank calls it with the same nq,
+ * k and `epoch` (1, 2, 3, ... per call).  inbox[g] = rank g's inbox as mapped in this process (own allocation for
+ * g == rank).  A shard may hold fewer than k rows (it publishes what it has).
+ * These are the only entry points that allocate device memory (an IPC-exportable cudaMalloc region).
+ * ------------------------------------------------------------------------------------------ */
+size_t rir_exchange_bytes(int G, int nq_max, int k_max);
+int rir_peer_alloc(size_t bytes, void** ptr);             /* zero-filled */
+int rir_peer_free(void* ptr);
+int rir_peer_export(void* ptr, void* handle64);           /* 64-byte cudaIpcMemHandle_t, host buffer */
+int rir_peer_open(const void* handle64, void** ptr);      /* in another process */
+int rir_peer_close(void* ptr);
+int rir_sim_topk_sharded(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                         int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
+                         void* workspace, size_t workspace_bytes, int path, void* stream, int G, int rank,
+                         uint32_t epoch, int nq_max, int k_max, void* const* inbox /* host array [G] */);
+
 /* alpha query expansion (skeleton reference/manus/1_SPARSE/sparse_model.py:374-405):
  *   acc[q,:] (+)= sum_{j<kq, idx_off <= ix[q,j] < idx_off+n_local} max(sc[q,j],0)^alpha * dequant(X[ix[q,j]-idx_off,:])
  * accumulates the contribution of the rows this shard owns (acc fp32 [nq,d], zero it first; all-reduce across shards). */

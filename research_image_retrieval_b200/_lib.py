@@ -41,6 +41,15 @@ SIGNATURES = {
     "rir_merge_topk_workspace": (c_size_t, [c_int, c_int, c_int]),
     "rir_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "rir_exchange_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "rir_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "rir_peer_free": (c_int, [c_void_p]),
+    "rir_peer_export": (c_int, [c_void_p, c_void_p]),
+    "rir_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "rir_peer_close": (c_int, [c_void_p]),
+    "rir_sim_topk_sharded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int,
+                                     ctypes.c_uint32, c_int, c_int, POINTER(c_void_p)]),
     "rir_aqe_accumulate": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_float, c_void_p, c_void_p]),
     "rir_aqe_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -138,9 +138,9 @@ extern "C" size_t rir_sim_topk_workspace(int nq, int64_t n_local, int d, int k, 
   return pl.total;
 }
 
-extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale,
-                            int nq, int64_t n_local, int d, int k, int64_t idx_offset, float* out_score,
-                            int32_t* out_idx, void* workspace, size_t workspace_bytes, int path, void* stream) {
+static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                         int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
+                         void* workspace, size_t workspace_bytes, int path, void* stream, const Exchange* ex) {
   if (int e = check_arch()) return e;
   const int esz = elem_size(dtype);
   RIR_REQUIRE(esz != 0, "sim_topk: dtype must be RIR_F32, RIR_BF16 or RIR_FP8E4M3 (got %d)", dtype);
@@ -162,7 +162,15 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
 
   RIR_REQUIRE(X, "sim_topk: null X");
   RIR_REQUIRE(n_local >= 1, "sim_topk: empty shard (n_local == 0) - give every rank at least one row");
+  const int k_req = k;
+  if (ex && k > n_local) k = (int)n_local;  // a shard shorter than k publishes what it has, padded to k_req
   RIR_REQUIRE(k <= n_local, "sim_topk: k=%d exceeds the shard size %lld (clamp k on the host)", k, (long long)n_local);
+  Exchange exl{};
+  if (ex) {
+    exl = *ex;
+    exl.k_push = k_req;
+    ex = &exl;
+  }
 
   SimPlan pl;
   if (!make_plan(nq, n_local, k, &pl)) {
@@ -174,7 +182,10 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     SimParams p{};
     p.Q = Q; p.X = X; p.q_scale = q_scale; p.x_scale = x_scale;
     p.nq = nq; p.q0 = 0; p.n = n_local; p.d = d; p.row_bytes = d * esz;
-    return launch_exact_scan(p, dtype, nq, k, idx_offset, out_score, out_idx, nullptr, st);
+    if (ex) p.ex = *ex;
+    if (int e = launch_exact_scan(p, dtype, nq, k, idx_offset, out_score, out_idx, nullptr, st)) return e;
+    if (ex) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
+    return RIR_OK;
   }
   RIR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
               "sim_topk: workspace must be non-null and 256-byte aligned");
@@ -203,7 +214,9 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
     p.cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
     p.cap = pl.cap;
     uint32_t* ovf = reinterpret_cast<uint32_t*>(ws + pl.off_ovf);
-    const bool use_stream = (path == RIR_PATH_STREAM) || dtype == RIR_F32 || (path == RIR_PATH_AUTO && gq <= 2);
+    const bool use_stream = (path == RIR_PATH_STREAM) || dtype == RIR_F32 || (path == RIR_PATH_AUTO && gq <= 2 && !mma_can_fuse(gq, n_local, k));
+    // (measured, 1M x 2048 bf16, 1 query: fused tcgen05 scan 1571 q/s vs stream 1500 q/s — same scan time, the fused
+    //  launch saves the separate sample / threshold passes)
 
     auto run_pass = [&](int mode) -> int {
       p.mode = mode;
@@ -224,6 +237,10 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
 
     p.nq = gq;
     p.k = k;
+    if (ex) {
+      p.ex = *ex;
+      p.ex.q_base = g0;
+    }
     p.gbar = p.cnt + align_up((size_t)pl.group, 128);  // right behind cnt[]
     p.tau_flag = p.gbar + 16;
     if (pl.scan_all) {
@@ -273,5 +290,79 @@ extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float
       if (int e = launch_exact_scan(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
     }
   }
+  // sharded: every rank's lists are on their way into the inboxes; wait for all G of them and merge
+  if (ex) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
   return RIR_OK;
+}
+
+extern "C" int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale,
+                            int nq, int64_t n_local, int d, int k, int64_t idx_offset, float* out_score,
+                            int32_t* out_idx, void* workspace, size_t workspace_bytes, int path, void* stream) {
+  return sim_topk_impl(Q, X, dtype, q_scale, x_scale, nq, n_local, d, k, idx_offset, out_score, out_idx, workspace,
+                       workspace_bytes, path, stream, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharded search over NVLink peer memory
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t rir_exchange_bytes(int G, int nq_max, int k_max) {
+  if (G < 1 || G > kMaxPeers || nq_max < 1 || k_max < 1) return 0;
+  return exchange_bytes(G, nq_max, k_max);
+}
+
+extern "C" int rir_peer_alloc(size_t bytes, void** ptr) {
+  if (int e = check_arch()) return e;
+  RIR_REQUIRE(ptr != nullptr && bytes > 0, "peer_alloc: bad arguments");
+  RIR_CUDA_OK(cudaMalloc(ptr, bytes));  // a plain cudaMalloc allocation: exportable with cudaIpcGetMemHandle
+  RIR_CUDA_OK(cudaMemset(*ptr, 0, bytes));
+  RIR_CUDA_OK(cudaDeviceSynchronize());
+  return RIR_OK;
+}
+
+extern "C" int rir_peer_free(void* ptr) {
+  if (ptr) RIR_CUDA_OK(cudaFree(ptr));
+  return RIR_OK;
+}
+
+extern "C" int rir_peer_export(void* ptr, void* handle64) {
+  RIR_REQUIRE(ptr && handle64, "peer_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  RIR_CUDA_OK(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return RIR_OK;
+}
+
+extern "C" int rir_peer_open(const void* handle64, void** ptr) {
+  RIR_REQUIRE(ptr && handle64, "peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  RIR_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RIR_OK;
+}
+
+extern "C" int rir_peer_close(void* ptr) {
+  if (ptr) RIR_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return RIR_OK;
+}
+
+extern "C" int rir_sim_topk_sharded(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale,
+                                    int nq, int64_t n_local, int d, int k, int64_t idx_offset, float* out_score,
+                                    int32_t* out_idx, void* workspace, size_t workspace_bytes, int path, void* stream,
+                                    int G, int rank, uint32_t epoch, int nq_max, int k_max, void* const* inbox) {
+  RIR_REQUIRE(G >= 1 && G <= kMaxPeers && rank >= 0 && rank < G, "sim_topk_sharded: bad rank %d of %d (<= %d ranks)", rank,
+              G, kMaxPeers);
+  RIR_REQUIRE(epoch != 0u, "sim_topk_sharded: epoch starts at 1");
+  RIR_REQUIRE(nq >= 0 && nq <= nq_max && k >= 1 && k <= k_max, "sim_topk_sharded: nq=%d k=%d exceed the inbox (%d, %d)",
+              nq, k, nq_max, k_max);
+  RIR_REQUIRE(inbox != nullptr, "sim_topk_sharded: null inbox table");
+  Exchange ex{};
+  ex.G = G; ex.rank = rank; ex.epoch = epoch; ex.nq_max = nq_max; ex.k_max = k_max; ex.q_base = 0;
+  for (int g = 0; g < G; ++g) {
+    RIR_REQUIRE(inbox[g] != nullptr, "sim_topk_sharded: inbox of rank %d is null", g);
+    ex.inbox[g] = reinterpret_cast<unsigned long long*>(inbox[g]);
+  }
+  if (nq == 0) return RIR_OK;
+  return sim_topk_impl(Q, X, dtype, q_scale, x_scale, nq, n_local, d, k, idx_offset, out_score, out_idx, workspace,
+                       workspace_bytes, path, stream, &ex);
 }

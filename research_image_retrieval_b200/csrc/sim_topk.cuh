@@ -23,6 +23,38 @@ constexpr int kSampleBlockRows = 256;  // rows per sample block == MMA tile N
 enum SimMode : int { kModeScanFilter = 0, kModeSample = 1, kModeScanAll = 2, kModeFused = 3 };
 constexpr int kFusedTopT = 8;  // keys kept per (query, first-phase tile) in the fused scan
 
+// Sharded search without a collective library call: every rank owns an INBOX in its HBM that all peers can write
+// over NVLink (CUDA IPC mappings).  The select kernel of rank r stores its sorted local top-k (global-index keys) into
+// slot r of every rank's inbox and then raises a per-(slot, query) flag to the call's epoch (release, system scope);
+// the merge kernel of each rank waits for the G flags of its query (acquire) and merges.  Two parities alternate so
+// a rank that is one call ahead never overwrites data a slower peer is still merging.
+constexpr int kMaxPeers = 16;
+struct Exchange {
+  int G;            // ranks (0 = no exchange: results go to out_score / out_idx)
+  int rank;
+  uint32_t epoch;   // call counter, identical on every rank, starts at 1
+  int nq_max, k_max;
+  int q_base;       // global query index of this launch's query 0
+  int k_push;       // list length every rank publishes (the global k; a shard shorter than k pads with 0 keys)
+  unsigned long long* inbox[kMaxPeers];  // inbox of rank g as mapped in THIS process
+};
+__host__ __device__ __forceinline__ size_t exchange_key_slots(int G, int nq_max, int k_max) {
+  return (size_t)2 * G * nq_max * k_max;
+}
+__host__ __device__ __forceinline__ size_t exchange_bytes(int G, int nq_max, int k_max) {
+  return exchange_key_slots(G, nq_max, k_max) * 8 + (size_t)2 * G * nq_max * 4;
+}
+// keys of (parity b, source rank g, query q) inside an inbox
+__host__ __device__ __forceinline__ unsigned long long* exchange_keys(unsigned long long* inbox, const Exchange& ex,
+                                                                      int b, int g, int q) {
+  return inbox + (((size_t)b * ex.G + g) * ex.nq_max + q) * ex.k_max;
+}
+__host__ __device__ __forceinline__ uint32_t* exchange_flag(unsigned long long* inbox, const Exchange& ex, int b, int g,
+                                                            int q) {
+  return reinterpret_cast<uint32_t*>(inbox + exchange_key_slots(ex.G, ex.nq_max, ex.k_max)) +
+         ((size_t)b * ex.G + g) * ex.nq_max + q;
+}
+
 struct SimParams {
   const void* Q;         // [nq, d]
   const void* X;         // [n, d]
@@ -56,6 +88,7 @@ struct SimParams {
   long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
   long long perm_n;      // number of database tiles
   int k;                 // top-k requested (the fused scan computes tau itself)
+  Exchange ex;           // sharded search: push the local top-k to the peers instead of writing out_score / out_idx
 };
 
 // first row of sample block j (strided over the whole shard so clustered / sorted databases are sampled fairly)
@@ -83,6 +116,7 @@ bool mma_can_fuse(int nq, long long n, int k);
 int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st);
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
+int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st);
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                       int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);
 

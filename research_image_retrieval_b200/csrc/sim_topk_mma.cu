@@ -684,7 +684,33 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoding a tensor map costs a few microseconds of host time per call; a search loop re-uses the same database and
+// query buffers, so the last few descriptors are kept per host thread.
+struct MapCacheEntry {
+  const void* base;
+  long long rows;
+  int d, dtype, box_rows;
+  CUtensorMap map;
+};
+static thread_local MapCacheEntry g_map_cache[8];
+static thread_local int g_map_cache_next = 0;
+
+static int make_rowmajor_map_uncached(CUtensorMap* m, const void* base, long long rows, int d, int dtype, int box_rows);
+
 static int make_rowmajor_map(CUtensorMap* m, const void* base, long long rows, int d, int dtype, int box_rows) {
+  for (const MapCacheEntry& e : g_map_cache)
+    if (e.base == base && e.rows == rows && e.d == d && e.dtype == dtype && e.box_rows == box_rows && base != nullptr) {
+      *m = e.map;
+      return RIR_OK;
+    }
+  if (int e = make_rowmajor_map_uncached(m, base, rows, d, dtype, box_rows)) return e;
+  MapCacheEntry& slot = g_map_cache[g_map_cache_next];
+  g_map_cache_next = (g_map_cache_next + 1) % 8;
+  slot = MapCacheEntry{base, rows, d, dtype, box_rows, *m};
+  return RIR_OK;
+}
+
+static int make_rowmajor_map_uncached(CUtensorMap* m, const void* base, long long rows, int d, int dtype, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");

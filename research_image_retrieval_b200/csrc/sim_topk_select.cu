@@ -156,6 +156,28 @@ __device__ __forceinline__ void write_sorted(const uint64_t* dst, int got, int k
   }
 }
 
+// Sharded search: store this rank's sorted top-k of query q (keys re-based to GLOBAL row indices, 0 = padding) into
+// slot `rank` of every rank's inbox, then publish it.  All threads of the block must call.
+__device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, const uint64_t* dst, int got, int k,
+                                                     long long idx_offset) {
+  const int b = (int)(ex.epoch & 1u);
+  const int qg = ex.q_base + q;
+  const int kp = ex.k_push;
+  for (int i = threadIdx.x; i < ex.G * kp; i += blockDim.x) {
+    const int g = i / kp, j = i - g * kp;
+    const uint64_t key = (j < got && j < k) ? dst[j] : 0ull;
+    uint64_t out = 0ull;
+    if (key != 0ull) out = make_key(key_score(key), (uint32_t)((long long)key_index(key) + idx_offset));
+    exchange_keys(ex.inbox[g], ex, b, ex.rank, qg)[j] = out;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < ex.G) {
+    uint32_t* f = exchange_flag(ex.inbox[threadIdx.x], ex, b, ex.rank, qg);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(ex.epoch) : "memory");
+  }
+}
+
 constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
 constexpr int kMaxRedo = 64;      // first-phase tiles per query that may need a re-score before the exact path takes over
 
@@ -254,7 +276,8 @@ __global__ void __launch_bounds__(kSelectThreads)
     auto key_at = [=](int i) -> unsigned long long { return c[i]; };
     got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
   }
-  write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, dst, got, k, idx_offset);
+  else write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
 }
 
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
@@ -339,7 +362,8 @@ __global__ void __launch_bounds__(kExactThreads)
   }
   block_bitonic_sort_desc(buf, bufcap);
   const int got = count < k ? count : k;
-  write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, buf, got, k, idx_offset);
+  else write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
 }
 
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
@@ -434,6 +458,51 @@ __global__ void __launch_bounds__(kSelectThreads)
   };
   const int got = block_select_topk(key_at, G * k, k, dst, kpad, &scr);
   write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+}
+
+// Sharded search, receiving side: wait until every rank has published query q for this epoch, then merge G sorted
+// lists of k keys out of this rank's own inbox.
+__global__ void __launch_bounds__(kSelectThreads)
+    merge_exchange_kernel(const Exchange ex, int k, int kpad, float* out_sc, int32_t* out_ix) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ SelectScratch scr;
+  const int q = blockIdx.x;
+  const int b = (int)(ex.epoch & 1u);
+  unsigned long long* mine = ex.inbox[ex.rank];
+  if ((int)threadIdx.x < ex.G) {
+    const uint32_t* f = exchange_flag(mine, ex, b, threadIdx.x, q);
+    const long long t0 = clock64();
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == ex.epoch) break;
+      __nanosleep(100);
+      if (clock64() - t0 > 20000000000ll) {
+        printf("librir: rank %d never received query %d of rank %d (epoch %u, saw %u)\n", ex.rank, q, (int)threadIdx.x,
+               ex.epoch, v);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned long long* base = mine + (size_t)b * ex.G * ex.nq_max * ex.k_max;
+  const int nq_max = ex.nq_max, k_max = ex.k_max;
+  auto key_at = [=](int i) -> unsigned long long {
+    const int g = i / k, j = i - g * k;
+    return __ldcg(base + ((size_t)g * nq_max + q) * k_max + j);
+  };
+  const int got = block_select_topk(key_at, ex.G * k, k, dst, kpad, &scr);
+  write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+}
+
+int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st) {
+  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  RIR_CUDA_OK(cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_exchange_kernel<<<nq, kSelectThreads, smem, st>>>(ex, k, kpad, out_score, out_idx);
+  RIR_LAUNCH_OK();
+  return RIR_OK;
 }
 
 }  // namespace rir

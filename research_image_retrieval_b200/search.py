@@ -268,8 +268,11 @@ def rank(query_features, gallery_features, k: Optional[int] = None, dtype: str =
 class ShardedDatabase:
     """Database rows sharded across the ranks of a process group (one process per GPU).
 
-    Each rank searches its shard (global indices via idx_offset); the packed [nq, k] candidates are all-gathered
-    (NCCL over NVLink on GPUs; gloo in the CPU plumbing tests) and merged by rir_merge_topk on every rank."""
+    Each rank searches its shard (global indices via idx_offset).  The one exchange step runs either
+      * over NVLink peer memory (`enable_peer_exchange`): the select kernel stores the local top-k straight into every
+        rank's inbox and a merge kernel waits for the G lists — rir_sim_topk_sharded, no collective call; or
+      * as an all-gather of the packed [nq, k] candidates (NCCL on GPUs, gloo in the CPU plumbing tests) followed by
+        rir_merge_topk on every rank."""
 
     def __init__(self, local: Database, group=None):
         import torch.distributed as dist
@@ -277,8 +280,89 @@ class ShardedDatabase:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._inbox = None       # this rank's inbox (device pointer, owned)
+        self._peers = None       # ctypes array [G] of inbox pointers as mapped here
+        self._opened = []        # IPC mappings to close
+        self._epoch = 0
+        self._nq_max = self._k_max = 0
 
-    def search(self, q_rows, q_scale, k: int, path: str = "auto"):
+    # ---- NVLink peer-memory exchange -----------------------------------------------------------
+    def enable_peer_exchange(self, nq_max: int, k_max: int) -> bool:
+        """Collective.  Allocates this rank's inbox, exchanges CUDA IPC handles through the process group and maps the
+        peers' inboxes.  Returns False (and leaves the all-gather path in place) for a single rank."""
+        import ctypes
+
+        import torch.distributed as dist
+        if self.world == 1:
+            return False
+        if self.world > 16:
+            raise ValueError("peer exchange supports at most 16 ranks")
+        lib = _lib.load()
+        dev = self.local.rows.device
+        with torch.cuda.device(dev):
+            nbytes = lib.rir_exchange_bytes(self.world, int(nq_max), int(k_max))
+            if nbytes == 0:
+                raise ValueError("bad exchange shape")
+            ptr = ctypes.c_void_p()
+            _lib.check(lib.rir_peer_alloc(nbytes, ctypes.byref(ptr)))
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(lib.rir_peer_export(ptr, handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            peers = (ctypes.c_void_p * self.world)()
+            for g, h in enumerate(handles):
+                if g == self.rank:
+                    peers[g] = ptr.value
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(lib.rir_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
+                    peers[g] = q.value
+                    self._opened.append(q)
+            dist.barrier(group=self.group)  # every inbox is mapped (and zeroed) before the first store into it
+        self._inbox, self._peers = ptr, peers
+        self._nq_max, self._k_max, self._epoch = int(nq_max), int(k_max), 0
+        return True
+
+    def close(self):
+        """Collective.  Unmaps the peers' inboxes and frees this rank's."""
+        import torch.distributed as dist
+        if self._inbox is None:
+            return
+        lib = _lib.load()
+        torch.cuda.synchronize(self.local.rows.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.local.rows.device):
+            for q in self._opened:
+                lib.rir_peer_close(q)
+            dist.barrier(group=self.group)
+            lib.rir_peer_free(self._inbox)
+        self._inbox, self._peers, self._opened = None, None, []
+
+    def _search_peer(self, q_rows, q_scale, k: int, path: str):
+        lib = _lib.load()
+        loc = self.local
+        nq = q_rows.shape[0]
+        k_local = min(k, loc.n)
+        check_k_supported(k_local, loc.n)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=loc.rows.device)
+        ix = torch.empty((nq, k), dtype=torch.int32, device=loc.rows.device)
+        ws = loc.workspace(nq, k_local)
+        self._epoch += 1
+        with torch.cuda.device(loc.rows.device):
+            _lib.check(lib.rir_sim_topk_sharded(
+                q_rows.data_ptr(), loc.rows.data_ptr(), _DTYPES[loc.dtype],
+                None if q_scale is None else q_scale.data_ptr(), None if loc.scale is None else loc.scale.data_ptr(),
+                nq, loc.n, loc.d, k, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), ws.data_ptr(), ws.numel(),
+                PATHS[path], _lib.stream_ptr(), self.world, self.rank, self._epoch, self._nq_max, self._k_max,
+                self._peers))
+        return sc, ix
+
+    def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto"):
+        """exchange: "auto" = peer memory when enabled and the batch fits the inbox, else all-gather; "nccl" forces the
+        all-gather + merge path."""
+        if (exchange != "nccl" and self._inbox is not None and 0 < q_rows.shape[0] <= self._nq_max
+                and k <= self._k_max and q_rows.is_contiguous()):
+            return self._search_peer(q_rows, q_scale, k, path)
         k_local = min(k, self.local.n)
         sc, ix = self.local.search(q_rows, q_scale, k_local, path=path)
         sc, ix = pad_topk(sc, ix, k)

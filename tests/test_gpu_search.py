@@ -153,8 +153,8 @@ def test_auto_path_and_grouping(cuda_device):
     qr, qs = db.pack_queries(Q.to(cuda_device))
     a = db.search(qr, qs, 20, path="auto")
     b = db.search(qr, qs, 20, path="stream")  # 9 queries -> two stream launches of 8 + 1
-    c = db.search(qr[:3].contiguous(), None, 20, path="auto")  # <= 4 queries -> stream
-    assert torch.equal(a[1], b[1]) and torch.equal(a[1][:3], c[1])
+    c = db.search(qr[:2].contiguous(), None, 20, path="auto")  # <= 2 queries on a small shard -> stream
+    assert torch.equal(a[1], b[1]) and torch.equal(a[1][:2], c[1])
     np.testing.assert_allclose(a[0].cpu().numpy(), b[0].cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
