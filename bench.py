@@ -311,11 +311,12 @@ def run_ours(args):
         pass
     stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2 and n_local < 2 * 148 * 256)
     kernel_name = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
-    traffic = None
+    traffic = None  # dram bytes of one scan launch from the committed ncu capture of the SAME configuration, else null
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("sim_scan_dram_bytes_per_launch" if not stream_path else
-                                       "sim_stream_dram_bytes_per_launch")
+            t = json.load(f).get(f"nq{args.nq}")
+        if t and world == 1 and not stream_path and (args.n, args.d, args.dtype) == (N_DB, DIM, "bf16"):
+            traffic = t["dram_bytes_per_launch"]
     except Exception:
         pass
     flops = 2.0 * args.nq * n_local * args.d
