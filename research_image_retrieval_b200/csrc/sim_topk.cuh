@@ -87,6 +87,7 @@ struct SimParams {
   int fused_tiles;       // first-phase tiles == slots per query in sample_keys / kFusedTopT
   long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
   long long perm_n;      // number of database tiles
+  int tile_rows;         // rows per database tile of the fused scan (256 or 128)
   int k;                 // top-k requested (the fused scan computes tau itself)
   Exchange ex;           // sharded search: push the local top-k to the peers instead of writing out_score / out_idx
 };

@@ -83,6 +83,7 @@ struct MmaGeom {
   int a_rows;         // query rows per block actually loaded (multiple of 8 * sharers; 128 unless one small block)
   int fused;          // kModeFused
   int ra_rounds;      // fused: rounds [0, ra_rounds) are the sample phase
+  int tile_n;         // database rows per tile: 256, or 128 when a small shard would leave the last round mostly idle
   int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue math
 };
 
@@ -286,10 +287,10 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
 
   // virtual tile -> first database row.  Dummy tiles (v >= ntiles) start past the last row (all-OOB loads).
   auto tile_row0 = [&](long long v) -> long long {
-    if (v >= g.ntiles) return ((p.n + kTileN - 1) / kTileN) * (long long)kTileN;
+    if (v >= g.ntiles) return ((p.n + g.tile_n - 1) / g.tile_n) * (long long)g.tile_n;
     if (p.mode == kModeSample) return sample_block_row0((int)v, p.nblk, p.sblk);
-    if (g.fused) return ((v * p.perm_mul) % p.perm_n) * (long long)kTileN;
-    return v * (long long)kTileN;
+    if (g.fused) return ((v * p.perm_mul) % p.perm_n) * (long long)g.tile_n;
+    return v * (long long)g.tile_n;
   };
 
   if (warp == 0) {
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_x));
       int s = 0;
       uint32_t ph = 0;
-      const int slice_rows = kTileN / cb, slice_bytes = kBBytes / cb;
+      const int slice_rows = g.tile_n / cb, slice_bytes = g.tile_n * 128 / cb;
+      const uint32_t b_bytes = (uint32_t)(g.tile_n * 128);
       for (long long rd = 0; rd < g.rounds; ++rd) {
         long long v;
         int sb;
@@ -310,11 +312,11 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           mbar_wait(&tail->empty_b[s], ph ^ 1u);
           uint8_t* dst = ring_b + (size_t)s * kBSlot;
           if (TWO) {  // my 128 rows into my shared memory; both halves complete on the leader's barrier
-            if (leader) mbar_expect_tx(&tail->full_b[s], kBBytes);
-            tma_tensor2d_g2s_2sm(dst, &tmX, kc * kElemsPerChunk, row0 + crank * (kTileN / 2),
+            if (leader) mbar_expect_tx(&tail->full_b[s], b_bytes);
+            tma_tensor2d_g2s_2sm(dst, &tmX, kc * kElemsPerChunk, row0 + crank * (g.tile_n / 2),
                                  mapa_u32(smem_u32(&tail->full_b[s]), 0), pol_x);
           } else {
-            mbar_expect_tx(&tail->full_b[s], kBBytes);
+            mbar_expect_tx(&tail->full_b[s], b_bytes);
             if (cb == 1)
               tma_tensor2d_g2s(dst, &tmX, kc * kElemsPerChunk, row0, &tail->full_b[s], pol_x);
             else  // my 1/cb of the rows, delivered to every CTA of the cluster
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       const int xb = (int)(rd & 1);
       const __nv_bfloat162 ts2 = __float2bfloat162_rn(ts);
       if (p.x_scale) {  // stage this tile's row scales (uniform branch)
-        for (int j = etid; j < kTileN; j += kEpiThreads) {
+        for (int j = etid; j < g.tile_n; j += kEpiThreads) {
           const long long row = row0 + j;
           tail->xs[xb][j] = row < p.n ? p.x_scale[row] : 0.f;
         }
@@ -626,12 +628,12 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         uint32_t va[16], vb[16];
         tmem_ld_32x32_x16(taddr, va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTileN; c0 += 32) {
+        for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
           tmem_ld_wait();
           tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 16), vb);
           process16(va, c0);
           tmem_ld_wait();
-          if (c0 + 32 < kTileN) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
+          if (c0 + 32 < g.tile_n) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
           process16(vb, c0 + 16);
         }
       }
@@ -814,11 +816,19 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     if (o == 1 || o == 2) mb = o;
   }
   g.nsb = (g.nqb + mb - 1) / mb;
-  g.ntiles = p.mode == kModeSample ? p.sblk : (p.n + kTileN - 1) / kTileN;
+  // Tile height: 256 rows.  128-row tiles were tried for small shards (8-way sharded cfg-2: 492 tiles / 148 CTAs =
+  // 3.3 -> 4 rounds) to shorten the under-filled last round, but measured SLOWER (scan 0.121 vs 0.106 ms at 125,916
+  // rows, 0.215 vs 0.172 ms at 251,831): the per-tile handshakes and epilogue outweigh the quantisation gain.
+  // Kept behind RIR_MMA_TILE128=1 for experiments.
+  g.tile_n = kTileN;
+  if (p.mode == kModeFused && g.nqb == 1 && (p.n + kTileN - 1) / kTileN < 8ll * sms &&
+      (p.n + 127) / 128 >= 2ll * sms && env_int("RIR_MMA_TILE128", 0) != 0)
+    g.tile_n = 128;
+  g.ntiles = p.mode == kModeSample ? p.sblk : (p.n + g.tile_n - 1) / g.tile_n;
   const int epc = dtype == RIR_BF16 ? 64 : 128;
   g.kchunks = (p.d + epc - 1) / epc;
   const uint32_t fmt = dtype == RIR_BF16 ? 1u : 0u;  // F16F32Format::BF16 = 1 ; MXF8F6F4Format::E4M3 = 0
-  g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+  g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.tile_n >> 3) << 17) |
             ((uint32_t)(kTileM >> 4) << 24);
   g.x_streamed_once = (g.nsb == 1);
   // ring depths: ~192 KB of shared memory either way
@@ -874,6 +884,7 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     p.fused_tiles = (int)grid;
     p.sample_m = (int)grid * kFusedTopT;
     p.perm_n = g.ntiles;
+    p.tile_rows = g.tile_n;
     long long mul = g.ntiles / grid;  // consecutive virtual tiles land ~ntiles/grid apart
     if (mul < 1) mul = 1;
     while (gcd_ll(mul, g.ntiles) != 1) ++mul;
@@ -882,7 +893,7 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   }
   CUtensorMap tmQ, tmX;
   if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, g.a_rows / ca)) return e;
-  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, kTileN / cb)) return e;
+  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, g.tile_n / cb)) return e;
   if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, grid, mb, two, st);
   return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, grid, mb, two, st);
 }

@@ -224,8 +224,8 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
     const int chunks = p.row_bytes >> 4;
     for (int r = 0; r < nredo; ++r) {
       const long long tile = ((long long)s_redo[r] * p.perm_mul) % p.perm_n;
-      const long long row0 = tile * kSampleBlockRows;
-      for (long long row = row0 + warp; row < row0 + kSampleBlockRows && row < p.n; row += nwarps) {
+      const long long row0 = tile * p.tile_rows;
+      for (long long row = row0 + warp; row < row0 + p.tile_rows && row < p.n; row += nwarps) {
         float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
         if (p.x_scale) s *= p.x_scale[row];
         if (lane == 0 && s >= ts_lo) {
