@@ -315,10 +315,105 @@ def test_full_size_properties(cuda_device, nq, path):
     rescored = torch.einsum("qkd,qd->qk", X[ixl].float(), qr.float())
     assert torch.allclose(sc, rescored, rtol=2e-4, atol=2e-6)
     # (5) exactness: nothing outside the list beats the k-th score by more than the bf16 tie epsilon
+    _nothing_better_outside(qr.float(), X, sc, ixl, 1e-3)
+
+
+def _unit_rows_gpu(n, d, gen, dev, dtype=torch.float32, chunk=131072):
+    out = torch.empty(n, d, device=dev, dtype=dtype)
+    for lo in range(0, n, chunk):
+        blk = torch.randn(min(chunk, n - lo), d, generator=gen, device=dev)
+        out[lo:lo + blk.shape[0]] = (blk / blk.norm(dim=1, keepdim=True)).to(dtype)
+    return out
+
+
+def _nothing_better_outside(Qf, X, sc, ixl, eps, chunk=131072):
+    """Exactness at full size: every row whose fp32 score beats the k-th returned score by more than eps (relative) IS
+    in the returned list (membership is checked per row, so fp32 accumulation-order noise at the bar cannot flip it)."""
     kth = sc[:, -1]
+    bar = kth + eps * kth.abs()
+    for lo in range(0, X.shape[0], chunk):
+        s = Qf @ X[lo:lo + chunk].float().t()
+        qi, ci = torch.nonzero(s > bar[:, None], as_tuple=True)
+        if qi.numel():
+            present = (ixl[qi] == (ci + lo)[:, None]).any(1)
+            assert bool(present.all()), f"rows in [{lo}, {lo + chunk}) beat the k-th score but are not in the list"
+
+
+def test_cfg3_gldv2_shape_with_alpha_qe(cuda_device):
+    """BASELINE cfg-3 size: 1,129 queries x 761,757 x 512-d bf16, top-100, alpha-QE (k=10, alpha=3), re-query.
+    Size-independent properties + GPU fp32 restatement of the QE formula."""
+    nq, n, d, k, kq, alpha = 1129, 761757, 512, 100, 10, 3.0
+    gen = torch.Generator(device=cuda_device).manual_seed(1003)
+    X = _unit_rows_gpu(n, d, gen, cuda_device, torch.bfloat16)
+    Q = _unit_rows_gpu(nq, d, gen, cuda_device)
+    planted = torch.randperm(n, generator=gen, device=cuda_device)[: nq * 4].reshape(nq, 4)
+    for r in range(0, nq, 64):  # 4 near-duplicates per query
+        rows = Q[r:r + 64, None, :] + torch.randn(min(64, nq - r), 4, d, generator=gen, device=cuda_device) * (0.5 / d ** 0.5)
+        X[planted[r:r + 64].reshape(-1)] = (rows / rows.norm(dim=2, keepdim=True)).reshape(-1, d).to(torch.bfloat16)
+    db = rir.Database(X, None, "bf16")
+    qr = Q.to(torch.bfloat16)
+    sc, ix = db.search(qr, None, k)
+    ixl = ix.long()
+    assert bool((sc[:, 1:] <= sc[:, :-1]).all())
+    assert all(len(set(ixl[r].tolist())) == k for r in range(0, nq, 37))
+    assert bool((torch.sort(ixl[:, :4], 1).values == torch.sort(planted, 1).values).all())
+    rescored = torch.einsum("qkd,qd->qk", X[ixl].float(), qr.float())
+    assert torch.allclose(sc, rescored, rtol=2e-4, atol=2e-6)
+    _nothing_better_outside(qr.float(), X, sc, ixl, 1e-3)
+    # alpha-QE: q' = L2(q + sum_j max(s_j,0)^alpha x_j) on the bf16-dequantised operands, fp32
+    q2, q2s, q2f = rir.alpha_query_expansion(db, qr, None, sc, ix, kq=kq, alpha=alpha)
+    w = sc[:, :kq].clamp(min=0).pow(alpha)
+    want = qr.float() + torch.einsum("qk,qkd->qd", w, X[ixl[:, :kq]].float())
+    want = want / want.norm(dim=1, keepdim=True)
+    assert torch.allclose(q2f, want, rtol=1e-4, atol=1e-6)
+    gathered = X[ixl[:8, :kq].reshape(-1)].float().cpu()  # the CPU oracle on the 80 rows the first 8 queries expand with
+    host = S.alpha_qe(qr[:8].float().cpu(), gathered, sc[:8].cpu().numpy(), np.arange(8 * kq).reshape(8, kq), kq, alpha)
+    np.testing.assert_allclose(q2f[:8].cpu().numpy(), host.numpy(), rtol=1e-4, atol=1e-6)
+    sc2, ix2 = db.search(q2, q2s, k)
+    assert bool((sc2[:, 1:] <= sc2[:, :-1]).all())
+    _nothing_better_outside(q2.float(), X, sc2, ix2.long(), 1e-3)
+    # expansion pulls the planted neighbours even closer: they stay on top
+    assert bool((torch.sort(ix2.long()[:, :4], 1).values == torch.sort(planted, 1).values).all())
+
+
+def test_cfg5_fp8_shape_subsample(cuda_device):
+    """BASELINE cfg-5 shape on one GPU: 1,580,470 x 2048 fp8 (+ per-row scales), top-10, 2,048-query subsample.
+    Bar: indices exact except ties within 5e-3 relative, judged on fp32 scores of the UNQUANTISED rows."""
+    nq, n, d, k = 2048, 1580470, 2048, 10
+    gen = torch.Generator(device=cuda_device).manual_seed(1005)
+    rows8 = torch.empty(n, d, device=cuda_device, dtype=torch.uint8)
+    scale = torch.empty(n, device=cuda_device)
+    rows16 = torch.empty(n, d, device=cuda_device, dtype=torch.bfloat16)
+    Q = _unit_rows_gpu(nq, d, gen, cuda_device)
+    planted = torch.randperm(n, generator=gen, device=cuda_device)[: nq * 3].reshape(nq, 3)
+    inv = torch.full((n,), -1, device=cuda_device, dtype=torch.long)
+    inv[planted.reshape(-1)] = torch.arange(nq * 3, device=cuda_device)
     for lo in range(0, n, 131072):
-        s = qr.float() @ X[lo:lo + 131072].float().t()
-        better = s > (kth * (1 + 1e-3))[:, None]
-        cnt = better.sum(1)
-        inlist = ((ixl >= lo) & (ixl < lo + 131072) & (sc > (kth * (1 + 1e-3))[:, None])).sum(1)
-        assert torch.equal(cnt, inlist)
+        blk = torch.randn(min(131072, n - lo), d, generator=gen, device=cuda_device)
+        hit = inv[lo:lo + blk.shape[0]]
+        sel = hit >= 0
+        if bool(sel.any()):
+            src = Q[hit[sel] // 3] + torch.randn(int(sel.sum()), d, generator=gen, device=cuda_device) * (0.5 / d ** 0.5)
+            blk[sel] = src
+        blk = blk / blk.norm(dim=1, keepdim=True)
+        r8, s8 = rir.pack_descriptors(blk, "fp8")
+        rows8[lo:lo + blk.shape[0]], scale[lo:lo + blk.shape[0]] = r8, s8
+        rows16[lo:lo + blk.shape[0]] = blk.to(torch.bfloat16)
+    db = rir.Database(rows8, scale, "fp8", rescore_rows=rows16)
+    sc, ix = db.query(Q, k)                      # fp8 scan for 2k+16 candidates, bf16 re-score
+    ixl = ix.long()
+    assert bool((sc[:, 1:] <= sc[:, :-1]).all())
+    assert bool((torch.sort(ixl[:, :3], 1).values == torch.sort(planted, 1).values).all())
+    # fp32 truth for a 256-query subsample, chunked
+    sub = torch.arange(0, nq, 8, device=cuda_device)
+    best_s = torch.full((sub.numel(), k), -1e30, device=cuda_device)
+    best_i = torch.zeros((sub.numel(), k), device=cuda_device, dtype=torch.long)
+    for lo in range(0, n, 262144):
+        s = Q[sub] @ rows16[lo:lo + 262144].float().t()
+        cs, ci = torch.cat([best_s, s], 1).topk(k, dim=1)
+        allidx = torch.cat([best_i, torch.arange(lo, lo + s.shape[1], device=cuda_device).expand(sub.numel(), -1)], 1)
+        best_s, best_i = cs, torch.gather(allidx, 1, ci)
+    got = ixl[sub].cpu().numpy()
+    true_of_got = torch.einsum("qkd,qd->qk", rows16[ixl[sub]].float(), Q[sub]).cpu().numpy()
+    ok, msg = S.indices_match_up_to_ties(got, true_of_got, best_i.cpu().numpy(), best_s.cpu().numpy(), 5e-3)
+    assert ok, msg
