@@ -90,6 +90,14 @@ int rir_l2_normalize(const float* x, int64_t n_rows, int d, float eps, float* ou
 int rir_whiten(const float* x, const float* W, const float* bias, int B, int C, int d_out, int l2_after, float* out,
                void* stream);
 
+/* PCA-whitening LEARN, dense part: column mean and covariance of descriptors X[N,D] (fp32, row-major):
+ *   mean[D] = X.mean(0);  cov[D,D] = (X - mean)^T (X - mean) / N   (exactly symmetric)
+ * Replaces networks/backbone.py:47-50 of pcawhitenlearn_shrinkage; the eigen-decomposition (:51-56) is done by the
+ * host (research_image_retrieval_b200/whitening.py) and its W, b feed rir_whiten (networks/spca.py:215-227). */
+size_t rir_pca_covariance_workspace(int64_t N, int D);
+int rir_pca_covariance(const float* X, int64_t N, int D, float* mean, float* cov, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Multi-scale aggregation of extract_vectors (utils/helpfunc.py:31-44): v[N,S,D] per-scale descriptors,
  * keep[N,S] (1 = scale used, 0 = dropped because the resized image was < 36 px; NULL = all kept);
  * out[n,:] = L2( sum_s keep*v[n,s,:] / #kept ). */

@@ -23,6 +23,7 @@ LIB = os.path.join(LIBDIR, "librir.so")
 SOURCES = [
     "rir_api.cu",
     "descriptor_build.cu",
+    "pca_whiten.cu",
     "sim_topk_stream.cu",
     "sim_topk_mma.cu",
     "sim_topk_select.cu",

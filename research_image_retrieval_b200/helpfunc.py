@@ -39,6 +39,21 @@ def extract_vectors(net, loader, ms=[1], device=torch.device('cuda'), print_freq
     Mirrors utils/helpfunc.py:18-48 including the tiny-image rules: single-scale inputs smaller than 36 px are
     upsampled so the short side is 64 (`:24-26`); in multi-scale mode a rescaled input smaller than 36 px is dropped
     from the mean (`:39-41`)."""
+    return extract_vectors_device(net, loader, ms, device, print_freq).cpu()
+
+
+@torch.no_grad()
+def extract_database(net, loader, ms=[1], device=torch.device('cuda'), print_freq=100, dtype="bf16", idx_offset=0):
+    """descriptors go from the network straight into the search layout (bf16 / fp8 + row scales) in
+    HBM — no host round trip between `extract_vectors` and the similarity scan.  Returns a `search.Database`."""
+    from .search import Database
+    return Database.from_descriptors(extract_vectors_device(net, loader, ms, device, print_freq), dtype,
+                                     idx_offset=idx_offset)
+
+
+@torch.no_grad()
+def extract_vectors_device(net, loader, ms=[1], device=torch.device('cuda'), print_freq=100):
+    """extract_vectors without the final device->host copy: fp32 [N, outputdim] on `device`."""
     net.eval()
     n = len(loader)
     D = net.outputdim
@@ -52,7 +67,7 @@ def extract_vectors(net, loader, ms=[1], device=torch.device('cuda'), print_freq
             if (i + 1) % print_freq == 0 or i + 1 == n:
                 print('\r>>>> {}/{} done...'.format(i + 1, n), end='')
         print('')
-        return vecs.cpu()
+        return vecs
     S = len(ms)
     per_scale = torch.zeros((n, S, D), dtype=torch.float32, device=device)
     keep = torch.zeros((n, S), dtype=torch.uint8)
@@ -69,4 +84,4 @@ def extract_vectors(net, loader, ms=[1], device=torch.device('cuda'), print_freq
         if (i + 1) % print_freq == 0 or i + 1 == n:
             print('\r>>>> {}/{} done...'.format(i + 1, n), end='')
     print('')
-    return scale_mean_l2(per_scale, keep).cpu()
+    return scale_mean_l2(per_scale, keep)

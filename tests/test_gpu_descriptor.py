@@ -138,6 +138,10 @@ def test_extract_vectors_golden(cuda_device, capsys):
     np.testing.assert_allclose(v1.numpy(), g["v_single"], rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(v3.numpy(), g["v_multi"], rtol=2e-4, atol=2e-5)
     assert ">>>> 4/4 done..." in capsys.readouterr().out
+    # the same descriptors, kept on the device and written straight into the search layout
+    db = rir.extract_database(net, images, [1, 2 ** 0.5, 2 ** -0.5], cuda_device, dtype="bf16", idx_offset=7)
+    assert db.rows.is_cuda and db.rows.dtype == torch.bfloat16 and db.n == 4 and db.idx_offset == 7
+    assert torch.equal(db.rows.cpu(), D.pack_bf16(v3))
 
 
 def test_pack_descriptors_bit_exact(cuda_device):
@@ -152,3 +156,39 @@ def test_pack_descriptors_bit_exact(cuda_device):
     assert tuple(rows.shape) == (50, 80)
     assert torch.equal(scale.cpu(), s)
     assert torch.equal(rows.cpu(), q.view(torch.uint8))
+
+
+def test_pca_whitening_learn(cuda_device):
+    """mean + covariance on the GPU (rir_pca_covariance), eigh on the host side; vs the oracle
+    restatement of pcawhitenlearn_shrinkage (networks/backbone.py:42-58), which is pinned to the reference."""
+    gen = torch.Generator().manual_seed(11)
+    N, Dm = 3000, 200                                   # D not a multiple of the 128-wide tile
+    scales = torch.logspace(0.5, -0.5, Dm)              # well separated eigenvalues
+    X = (torch.randn(N, Dm, generator=gen) * scales + torch.linspace(-1, 1, Dm)).numpy().astype(np.float32)
+    mean, cov = rir.pca_covariance(torch.from_numpy(X).to(cuda_device))
+    Xd = X.astype(np.float64)
+    mref = Xd.mean(0)
+    cref = (Xd - mref).T @ (Xd - mref) / N
+    np.testing.assert_allclose(mean.cpu().numpy(), mref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(cov.cpu().numpy(), cref, rtol=2e-4, atol=2e-5)
+    assert torch.equal(cov, cov.t())                    # exactly symmetric, like (Xcov + Xcov.T) / 2
+    m, Pt = rir.pcawhitenlearn_shrinkage(X)
+    m_ref, Pt_ref = D.pca_whiten_learn(Xd)
+    assert m.shape == (1, Dm) and Pt.shape == (Dm, Dm) and m.dtype == np.float32
+    np.testing.assert_allclose(m, m_ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.abs(Pt), np.abs(Pt_ref), rtol=5e-3, atol=5e-3)   # eigenvector sign is free
+    Y = (Xd - m_ref) @ Pt.astype(np.float64)
+    np.testing.assert_allclose(np.cov(Y.T, bias=True), np.eye(Dm), atol=5e-3)      # whitened
+    # the layer the descriptor head consumes (networks/spca.py:215-227), dim reduction 200 -> 64
+    layer = rir.ConvDimReduction(Dm, 64).to(cuda_device)
+    layer.initialize_pca_whitening(X)
+    W_ref, b_ref = D.whitening_layer_from_pca(Xd, 64)
+    sign = torch.sign((layer.weight.data.reshape(64, Dm).cpu() * W_ref).sum(1))
+    np.testing.assert_allclose((layer.weight.data.reshape(64, Dm).cpu() * sign[:, None]).numpy(), W_ref.numpy(), rtol=5e-3,
+                               atol=5e-3)
+    np.testing.assert_allclose((layer.bias.data.cpu() * sign).numpy(), b_ref.numpy(), rtol=5e-3, atol=5e-3)
+    # and applied: whitened + L2 descriptors agree with the oracle's up to the per-component sign
+    x = torch.from_numpy(X[:32]).to(cuda_device)
+    got = rir.whiten(x, layer.weight, layer.bias, l2_after=True).cpu() * sign
+    want = D.l2n(D.whiten(torch.from_numpy(X[:32]), W_ref, b_ref))
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=5e-3, atol=5e-4)

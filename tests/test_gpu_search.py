@@ -417,3 +417,21 @@ def test_cfg5_fp8_shape_subsample(cuda_device):
     true_of_got = torch.einsum("qkd,qd->qk", rows16[ixl[sub]].float(), Q[sub]).cpu().numpy()
     ok, msg = S.indices_match_up_to_ties(got, true_of_got, best_i.cpu().numpy(), best_s.cpu().numpy(), 5e-3)
     assert ok, msg
+
+
+def test_descriptor_store_to_sharded_search(cuda_device, tmp_path):
+    """shard files on disk -> per-rank resident shards -> merged result == unsharded search."""
+    nq, n, d, k = 5, 30000, 64, 20
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=77)
+    rows, _ = rir.pack_descriptors(X.to(cuda_device), "bf16")
+    st = rir.DescriptorStore.create(str(tmp_path / "store"), rows.shape[1], "bf16")
+    for a, b in [(0, 9000), (9000, 9001), (9001, 30000)]:
+        st.append(rows[a:b])
+    whole = rir.Database(rows, None, "bf16")
+    qr, qs = whole.pack_queries(Q.to(cuda_device))
+    want_sc, want_ix = whole.search(qr, qs, k)
+    parts = [rir.DescriptorStore(str(tmp_path / "store")).load_database(4, r, cuda_device) for r in range(4)]
+    assert [p.idx_offset for p in parts] == [0, 7500, 15000, 22500] and sum(p.n for p in parts) == n
+    res = [p.search(qr, qs, k) for p in parts]
+    ms, mi = rir.merge_topk(torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res]))
+    assert torch.equal(mi, want_ix) and torch.equal(ms, want_sc)

@@ -93,3 +93,54 @@ def test_merge_topk_host_matches_oracle():
 def test_pad_topk():
     sc, ix = search.pad_topk(torch.ones(2, 3), torch.ones(2, 3, dtype=torch.int32), 5)
     assert tuple(sc.shape) == (2, 5) and torch.isinf(sc[:, 3:]).all() and (ix[:, 3:] == -1).all()
+
+
+def test_formats_gnd_loader_and_descriptor_store(tmp_path):
+    """the gnd pickle loader (dataset/configdataset.py:27-57) and the sharded descriptor store."""
+    import pickle
+
+    import torch
+
+    from research_image_retrieval_b200 import formats
+    from research_image_retrieval_b200.search import shard_bounds
+
+    # gnd_{dataset}.pkl as revisitop ships it: imlist, qimlist, gnd (list of dicts with bbx / easy / hard / junk)
+    d = tmp_path / "roxford5k"
+    d.mkdir()
+    gnd = [{"bbx": [0, 0, 1, 1], "easy": [3, 1], "hard": [7], "junk": [2, 9]}, {"bbx": [0, 0, 1, 1], "easy": [], "hard": [4]}]
+    with open(d / "gnd_roxford5k.pkl", "wb") as f:
+        pickle.dump({"imlist": [f"im{i}" for i in range(10)], "qimlist": ["q0", "q1"], "gnd": gnd}, f)
+    cfg = formats.RoxfordAndRparis("ROxford5k", str(tmp_path))
+    assert cfg["n"] == 10 and cfg["nq"] == 2 and cfg["dataset"] == "roxford5k"
+    assert cfg["im_fname"][3].endswith("roxford5k/jpg/im3.jpg") and cfg["qim_fname"][1].endswith("q1.jpg")
+    with pytest.raises(ValueError):
+        formats.RoxfordAndRparis("holidays", str(tmp_path))
+    csr = formats.gnd_to_csr(cfg["gnd"])
+    assert csr["easy"][0].tolist() == [1, 3] and csr["easy"][1].tolist() == [0, 2, 2]
+    assert csr["junk"][0].tolist() == [2, 9] and csr["junk"][1].tolist() == [0, 2, 2]   # missing 'junk' -> empty
+
+    # descriptor store: 3 uneven shard files, read back across shard boundaries
+    gen = torch.Generator().manual_seed(0)
+    rows = torch.randn(1000, 16, generator=gen).to(torch.bfloat16)
+    st = formats.DescriptorStore.create(str(tmp_path / "r1m"), 16, "bf16")
+    for a, b in [(0, 300), (300, 301), (301, 1000)]:
+        st.append(rows[a:b])
+    st2 = formats.DescriptorStore(str(tmp_path / "r1m"))
+    assert st2.n == 1000 and st2.dim == 16 and len(st2.shards) == 3
+    for world in (1, 3, 8):
+        for rank in range(world):
+            lo, hi = shard_bounds(1000, world, rank)
+            got, sc = st2.load_rows(lo, hi)
+            assert sc is None and torch.equal(got, rows[lo:hi])
+    with pytest.raises(ValueError):
+        st2.load_rows(0, 1001)
+    # fp8 shards carry their per-row scales
+    s8 = formats.DescriptorStore.create(str(tmp_path / "r1m_fp8"), 16, "fp8")
+    q8 = torch.randint(0, 255, (50, 16), dtype=torch.uint8)
+    sc8 = torch.rand(50)
+    s8.append(q8[:20], sc8[:20])
+    s8.append(q8[20:], sc8[20:])
+    got, sc = formats.DescriptorStore(str(tmp_path / "r1m_fp8")).load_rows(10, 45)
+    assert torch.equal(got, q8[10:45]) and torch.equal(sc, sc8[10:45])
+    with pytest.raises(ValueError):
+        s8.append(q8[:5])
