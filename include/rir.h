@@ -172,6 +172,17 @@ int rir_sim_topk_sharded(const void* Q, const void* X, int dtype, const float* q
                          void* workspace, size_t workspace_bytes, int path, void* stream, int G, int rank,
                          uint32_t epoch, int nq_max, int k_max, void* const* inbox /* host array [G] */);
 
+/* The whole query path as one call on HOST buffers (what the reference call site holds: CPU fp32 query features,
+ * iris_evaluate.py:378-386): H2D of q_host[nq,d] fp32 (pinned memory recommended) -> pack to the shard's dtype ->
+ * rir_sim_topk (or rir_sim_topk_sharded when G > 1; pass G = 1, inbox = NULL otherwise) -> D2H of the top-k into
+ * out_score_host / out_idx_host [nq,k].  Everything is enqueued on `stream`; synchronise the stream before reading
+ * the outputs.  d must already be a multiple of 16 bytes in the shard's dtype.  Without exchange k <= n_local. */
+size_t rir_search_host_workspace(int nq, int64_t n_local, int d, int k, int dtype);
+int rir_search_host(const float* q_host, const void* X, int dtype, const float* x_scale, int nq, int64_t n_local, int d,
+                    int k, int64_t idx_offset, float* out_score_host, int32_t* out_idx_host, void* workspace,
+                    size_t workspace_bytes, int path, void* stream, int G, int rank, uint32_t epoch, int nq_max,
+                    int k_max, void* const* inbox);
+
 /* alpha query expansion (skeleton reference/manus/1_SPARSE/sparse_model.py:374-405):
  *   acc[q,:] (+)= sum_{j<kq, idx_off <= ix[q,j] < idx_off+n_local} max(sc[q,j],0)^alpha * dequant(X[ix[q,j]-idx_off,:])
  * accumulates the contribution of the rows this shard owns (acc fp32 [nq,d], zero it first; all-reduce across shards). */

@@ -52,6 +52,10 @@ SIGNATURES = {
     "rir_sim_topk_sharded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int,
                                      ctypes.c_uint32, c_int, c_int, POINTER(c_void_p)]),
+    "rir_search_host_workspace": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
+    "rir_search_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, ctypes.c_uint32, c_int, c_int,
+                                POINTER(c_void_p)]),
     "rir_aqe_accumulate": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_float, c_void_p, c_void_p]),
     "rir_aqe_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

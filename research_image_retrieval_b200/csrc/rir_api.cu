@@ -1,6 +1,7 @@
 // rir_api.cu — C-ABI glue: error state, device checks and the sim_topk orchestration
 // (sample -> threshold -> scan -> select -> overflow fallback; see sim_topk.cuh).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "sim_topk.cuh"
 #include "topk_select.cuh"
@@ -285,8 +286,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     float* os = out_score + (size_t)g0 * k;
     int32_t* oi = out_idx + (size_t)g0 * k;
     if (int e = launch_final_select(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
-    if (!pl.scan_all) {
-      // queries whose candidate list overflowed (adversarial row order) are redone exactly; no-op otherwise
+    if (!pl.scan_all && !select_handles_overflow(k)) {
+      // very large k: queries whose candidate list overflowed are redone by the separate exact kernel (no-op otherwise)
       if (int e = launch_exact_scan(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
     }
   }
@@ -365,4 +366,108 @@ extern "C" int rir_sim_topk_sharded(const void* Q, const void* X, int dtype, con
   if (nq == 0) return RIR_OK;
   return sim_topk_impl(Q, X, dtype, q_scale, x_scale, nq, n_local, d, k, idx_offset, out_score, out_idx, workspace,
                        workspace_bytes, path, stream, &ex);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry point: the whole query path as ONE call (the reference call site hands over CPU tensors:
+// iris_evaluate.py:378-386 works on `query_features` that come out of extract_vectors as CPU fp32)
+// ---------------------------------------------------------------------------------------------
+struct HostPlan {
+  size_t off_qf, off_qp, off_qs, off_sc, off_ix, off_sim, total;
+};
+static bool make_host_plan(int nq, int64_t n_local, int d, int k, int dtype, HostPlan* hp) {
+  const int esz = elem_size(dtype);
+  if (esz == 0 || nq < 1 || d < 1 || k < 1) return false;
+  long long kk = k;
+  if (kk > n_local) kk = n_local;
+  const size_t sim = rir_sim_topk_workspace(nq, n_local, d, (int)kk, dtype);
+  if (sim == 0) return false;
+  size_t o = 0;
+  hp->off_sim = o; o = align_up(o + sim, 256);
+  hp->off_qf = o;  o = align_up(o + (size_t)nq * d * 4, 256);
+  hp->off_qp = o;  o = align_up(o + (size_t)nq * d * esz, 256);
+  hp->off_qs = o;  o = align_up(o + (size_t)nq * 4, 256);
+  hp->off_sc = o;  o = align_up(o + (size_t)nq * k * 4, 256);
+  hp->off_ix = o;  o = align_up(o + (size_t)nq * k * 4, 256);
+  hp->total = o;
+  return true;
+}
+
+extern "C" size_t rir_search_host_workspace(int nq, int64_t n_local, int d, int k, int dtype) {
+  HostPlan hp;
+  return make_host_plan(nq, n_local, d, k, dtype, &hp) ? hp.total : 0;
+}
+
+extern "C" int rir_search_host(const float* q_host, const void* X, int dtype, const float* x_scale, int nq,
+                               int64_t n_local, int d, int k, int64_t idx_offset, float* out_score_host,
+                               int32_t* out_idx_host, void* workspace, size_t workspace_bytes, int path, void* stream,
+                               int G, int rank, uint32_t epoch, int nq_max, int k_max, void* const* inbox) {
+  if (int e = check_arch()) return e;
+  RIR_REQUIRE(q_host && out_score_host && out_idx_host, "search_host: null host buffer");
+  RIR_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "search_host: workspace must be 256-byte aligned");
+  if (nq == 0) return RIR_OK;
+  HostPlan hp;
+  if (!make_host_plan(nq, n_local, d, k, dtype, &hp)) {
+    set_error("search_host: unsupported shape nq=%d n=%lld d=%d k=%d dtype=%d", nq, (long long)n_local, d, k, dtype);
+    return RIR_E_ARG;
+  }
+  if (workspace_bytes < hp.total) {
+    set_error("search_host: workspace of %zu B is smaller than the required %zu B", workspace_bytes, hp.total);
+    return RIR_E_WORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* qf = reinterpret_cast<float*>(ws + hp.off_qf);
+  void* qp = ws + hp.off_qp;
+  float* qs = reinterpret_cast<float*>(ws + hp.off_qs);
+  float* sc = reinterpret_cast<float*>(ws + hp.off_sc);
+  int32_t* ix = reinterpret_cast<int32_t*>(ws + hp.off_ix);
+  // Pinned (page-locked) host buffers are device-accessible under UVA: the pack kernel then reads the queries
+  // straight from host memory and the select / merge kernel writes the top-k straight into the caller's buffers —
+  // no copy launches on the critical path.  Pageable buffers take the cudaMemcpyAsync route.
+  auto device_view = [](const void* host) -> void* {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+  };
+  // bit 0: queries read in place, bit 1: results written in place (development override RIR_HOST_ZERO_COPY)
+  static const int zero_copy = getenv("RIR_HOST_ZERO_COPY") ? atoi(getenv("RIR_HOST_ZERO_COPY")) : 2;
+  const float* q_dev_view =
+      ((zero_copy & 1) && dtype != RIR_F32) ? reinterpret_cast<const float*>(device_view(q_host)) : nullptr;
+  float* sc_dev_view = (zero_copy & 2) ? reinterpret_cast<float*>(device_view(out_score_host)) : nullptr;
+  int32_t* ix_dev_view = (zero_copy & 2) ? reinterpret_cast<int32_t*>(device_view(out_idx_host)) : nullptr;
+  const bool direct_out = sc_dev_view != nullptr && ix_dev_view != nullptr;
+  if (direct_out) {
+    sc = sc_dev_view;
+    ix = ix_dev_view;
+  }
+  const float* q_src = q_dev_view;
+  if (q_src == nullptr) {
+    RIR_CUDA_OK(cudaMemcpyAsync(qf, q_host, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st));
+    q_src = qf;
+  }
+  const void* Q = q_src;
+  const float* q_scale = nullptr;
+  if (dtype != RIR_F32) {
+    if (int e = rir_pack_descriptors(q_src, nq, d, dtype, qp, qs, stream)) return e;
+    Q = qp;
+    if (dtype == RIR_FP8E4M3) q_scale = qs;
+  }
+  const size_t sim_bytes = hp.off_qf;  // the region in front of the staging buffers
+  int rc;
+  if (G > 1)
+    rc = rir_sim_topk_sharded(Q, X, dtype, q_scale, x_scale, nq, n_local, d, k, idx_offset, sc, ix, ws + hp.off_sim,
+                              sim_bytes, path, stream, G, rank, epoch, nq_max, k_max, inbox);
+  else
+    rc = rir_sim_topk(Q, X, dtype, q_scale, x_scale, nq, n_local, d, k, idx_offset, sc, ix, ws + hp.off_sim, sim_bytes,
+                      path, stream);
+  if (rc) return rc;
+  if (!direct_out) {
+    RIR_CUDA_OK(cudaMemcpyAsync(out_score_host, sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    RIR_CUDA_OK(cudaMemcpyAsync(out_idx_host, ix, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+  }
+  return RIR_OK;
 }

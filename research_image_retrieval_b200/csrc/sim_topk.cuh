@@ -117,6 +117,7 @@ bool mma_can_fuse(int nq, long long n, int k);
 int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st);
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
+bool select_handles_overflow(int k);  // the select kernel redoes overflowed queries itself (no fallback launch needed)
 int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st);
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                       int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);

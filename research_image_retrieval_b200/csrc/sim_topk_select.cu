@@ -178,6 +178,61 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// robust exact scan of ONE query by one CTA: running top-k in shared memory.  Used (a) for queries whose candidate
+// list overflowed — called from the select kernel itself, so the common no-overflow case costs no extra launch —
+// and (b) as RIR_PATH_EXACT, an independent second implementation for the parity tests.
+// ---------------------------------------------------------------------------------------------
+// running-buffer size of the exact redo inside the select kernel: a power of two with room for k survivors plus two
+// iterations of pushes (kSelectThreads / 32 warps x 4 rows each)
+__host__ __device__ __forceinline__ int inline_exact_bufcap(int k) {
+  const int need = k + 2 * (kSelectThreads / 32) * 4;
+  int c = 64;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+template <int DT>
+__device__ void exact_scan_body(const SimParams& p, int q, int k, int bufcap, uint64_t* buf, float* qs,
+                                long long idx_offset, float* out_score, int32_t* out_idx) {
+  __shared__ int count;
+  __shared__ unsigned long long tau;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_iter = (int)(blockDim.x >> 5) * 4;  // 4 rows per warp and iteration
+  load_query_f32<DT>(p, q, qs);
+  for (int i = threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
+  if (threadIdx.x == 0) { count = 0; tau = 0ull; }
+  __syncthreads();
+  const int chunks = p.row_bytes >> 4;
+  for (long long base = 0; base < p.n; base += rows_per_iter) {
+    const unsigned long long t = tau;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long row = base + warp * 4 + r;
+      if (row < p.n) {
+        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
+        if (p.x_scale) s *= p.x_scale[row];
+        const unsigned long long key = make_key(s, (uint32_t)row);
+        if (lane == 0 && key > t) buf[atomicAdd(&count, 1)] = key;
+      }
+    }
+    __syncthreads();
+    if (count > bufcap - rows_per_iter) {  // uniform branch: compact to the best k
+      block_bitonic_sort_desc(buf, bufcap);
+      if (threadIdx.x == 0 && count >= k) {
+        count = k;
+        tau = buf[k - 1];
+      }
+      for (int i = k + threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
+    }
+    __syncthreads();
+  }
+  block_bitonic_sort_desc(buf, bufcap);
+  const int got = count < k ? count : k;
+  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, buf, got, k, idx_offset);
+  else write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+}
+
 constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
 constexpr int kMaxRedo = 64;      // first-phase tiles per query that may need a re-score before the exact path takes over
 
@@ -247,7 +302,7 @@ __global__ void __launch_bounds__(kSelectThreads)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
   uint64_t* stage = dst + kpad;                            // [kStageKeys]
-  float* qs = reinterpret_cast<float*>(stage + kStageKeys);  // [d] (fused mode only)
+  float* qs = reinterpret_cast<float*>(stage + kStageKeys);  // [d] (first-phase redo / exact redo)
   __shared__ SelectScratch sc;
   __shared__ uint32_t s_extra;
   __shared__ int s_nredo;
@@ -259,8 +314,15 @@ __global__ void __launch_bounds__(kSelectThreads)
     ok = merge_first_phase<DT>(p, q, &cnt, qs, &s_extra, &s_nredo, s_redo);
     ok = ok && cnt <= (uint32_t)p.cap;
   }
-  if (!ok) {  // candidate list overflowed: the exact fallback kernel owns this query
-    if (threadIdx.x == 0) ovf[q] = 1u;
+  if (!ok) {  // candidate list overflowed (adversarial row order): redo this query exactly
+    const int bufcap = inline_exact_bufcap(k);
+    if (bufcap <= kStageKeys) {  // right here, no extra launch
+      if (threadIdx.x == 0) ovf[q] = 0u;
+      __syncthreads();
+      exact_scan_body<DT>(p, q, k, bufcap, stage, qs, idx_offset, out_score, out_idx);
+    } else if (threadIdx.x == 0) {
+      ovf[q] = 1u;  // very large k: the separate exact kernel owns this query
+    }
     return;
   }
   if (threadIdx.x == 0) ovf[q] = 0u;
@@ -280,10 +342,12 @@ __global__ void __launch_bounds__(kSelectThreads)
   else write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
 }
 
+bool select_handles_overflow(int k) { return inline_exact_bufcap(k) <= kStageKeys; }
+
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
-  const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t) + (p.mode == kModeFused ? (size_t)p.d * sizeof(float) : 0);
+  const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t) + (size_t)p.d * sizeof(float);
   if (smem > 220 * 1024) {
     set_error("sim_topk(select): k=%d d=%d needs %zu B of shared memory", k, p.d, smem);
     return RIR_E_ARG;
@@ -318,52 +382,7 @@ __global__ void __launch_bounds__(kExactThreads)
   if (ovf != nullptr && ovf[q] == 0u) return;
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);           // [bufcap]
   float* qs = reinterpret_cast<float*>(buf + bufcap);              // [d]
-  __shared__ int count;
-  __shared__ unsigned long long tau;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.d; i += blockDim.x) {
-    float v;
-    if (DT == RIR_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.Q)[(size_t)q * p.d + i]);
-    else if (DT == RIR_F32) v = reinterpret_cast<const float*>(p.Q)[(size_t)q * p.d + i];
-    else {
-      const __half_raw h =
-          __nv_cvt_fp8_to_halfraw(reinterpret_cast<const __nv_fp8_storage_t*>(p.Q)[(size_t)q * p.d + i], __NV_E4M3);
-      v = __half2float(*reinterpret_cast<const __half*>(&h));
-    }
-    if (p.q_scale) v *= p.q_scale[q];
-    qs[i] = v;
-  }
-  for (int i = threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
-  if (threadIdx.x == 0) { count = 0; tau = 0ull; }
-  __syncthreads();
-  const int chunks = p.row_bytes >> 4;
-  for (long long base = 0; base < p.n; base += kExactRowsPerIter) {
-    const unsigned long long t = tau;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const long long row = base + warp * 4 + r;
-      if (row < p.n) {
-        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
-        if (p.x_scale) s *= p.x_scale[row];
-        const unsigned long long key = make_key(s, (uint32_t)row);
-        if (lane == 0 && key > t) buf[atomicAdd(&count, 1)] = key;
-      }
-    }
-    __syncthreads();
-    if (count > bufcap - kExactRowsPerIter) {  // uniform branch: compact to the best k
-      block_bitonic_sort_desc(buf, bufcap);
-      if (threadIdx.x == 0 && count >= k) {
-        count = k;
-        tau = buf[k - 1];
-      }
-      for (int i = k + threadIdx.x; i < bufcap; i += blockDim.x) buf[i] = 0ull;
-    }
-    __syncthreads();
-  }
-  block_bitonic_sort_desc(buf, bufcap);
-  const int got = count < k ? count : k;
-  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, buf, got, k, idx_offset);
-  else write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+  exact_scan_body<DT>(p, q, k, bufcap, buf, qs, idx_offset, out_score, out_idx);
 }
 
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,

@@ -160,6 +160,36 @@ class Database:
         return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
                         idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k))
 
+    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
+        """The host-facing call: fp32 CPU queries [nq, d] (pinned for an asynchronous copy) -> top-k in host buffers.
+
+        One C-ABI call (rir_search_host) enqueues H2D -> pack -> search -> D2H on the current stream; this method
+        synchronises the stream and returns (scores [nq, k] fp32, idx [nq, k] int32) CPU tensors (`out` to re-use
+        pinned result buffers)."""
+        if q_host.is_cuda or q_host.dtype != torch.float32 or q_host.dim() != 2 or not q_host.is_contiguous():
+            raise TypeError("query_host expects a contiguous float32 CPU tensor [nq, d]")
+        nq, d = q_host.shape
+        if d != self.d or self.rescore_rows is not None:
+            raise ValueError("query_host needs d == the packed row width and no rescoring copy; use query()")
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.float32).pin_memory(), torch.empty((nq, k), dtype=torch.int32).pin_memory())
+        sc, ix = out
+        lib = _lib.load()
+        dt = _DTYPES[self.dtype]
+        need = lib.rir_search_host_workspace(nq, self.n, d, k, dt)
+        if need == 0:
+            raise ValueError(f"unsupported search shape nq={nq} n={self.n} d={d} k={k}")
+        if getattr(self, "_ws_host", None) is None or self._ws_host.numel() < need:
+            self._ws_host = torch.empty(need, dtype=torch.uint8, device=self.rows.device)
+        ex = _exchange or (1, 0, 0, 0, 0, None)
+        with torch.cuda.device(self.rows.device):
+            _lib.check(lib.rir_search_host(q_host.data_ptr(), self.rows.data_ptr(), dt,
+                                           None if self.scale is None else self.scale.data_ptr(), nq, self.n, d, k,
+                                           self.idx_offset, sc.data_ptr(), ix.data_ptr(), self._ws_host.data_ptr(),
+                                           self._ws_host.numel(), PATHS[path], _lib.stream_ptr(), *ex))
+            torch.cuda.current_stream().synchronize()
+        return sc, ix
+
     def query(self, q: torch.Tensor, k: int, path: str = "auto"):
         """fp32 queries [nq, d_logical] -> top-k.  With a rescoring copy: fp8 scan for 2k+16 candidates, then a bf16
         re-score of those rows (rir_rescore_topk) decides the final k."""
@@ -356,6 +386,16 @@ class ShardedDatabase:
                 PATHS[path], _lib.stream_ptr(), self.world, self.rank, self._epoch, self._nq_max, self._k_max,
                 self._peers))
         return sc, ix
+
+    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
+        """Database.query_host over the sharded database (peer exchange must be enabled for world > 1)."""
+        if self.world == 1:
+            return self.local.query_host(q_host, k, out=out, path=path)
+        if self._inbox is None or q_host.shape[0] > self._nq_max or k > self._k_max:
+            raise ValueError("enable_peer_exchange(nq_max, k_max) first (and keep nq, k within it)")
+        self._epoch += 1
+        return self.local.query_host(q_host, k, out=out, path=path,
+                                     _exchange=(self.world, self.rank, self._epoch, self._nq_max, self._k_max, self._peers))
 
     def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto"):
         """exchange: "auto" = peer memory when enabled and the batch fits the inbox, else all-gather; "nccl" forces the

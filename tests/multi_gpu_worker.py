@@ -50,6 +50,10 @@ def main():
         sc2, ix2 = sdb.search(q2, s2, min(k, n))
         w_sc2, w_ix2 = sdb.search(q2, s2, min(k, n), exchange="nccl")
         assert torch.equal(ix2, w_ix2) and torch.equal(sc2, w_sc2), f"case {ci}: 2-query batch differs"
+        if dtype != "fp32" or True:  # the host-buffer call over the exchange: same answer, CPU tensors
+            if db.d == d:
+                hs, hi_ = sdb.query_host(Q.contiguous().pin_memory(), min(k, n))
+                assert torch.equal(hi_, want_ix.cpu()) and torch.equal(hs, want_sc.cpu()), f"case {ci}: query_host differs"
         if rank == 0:  # oracle on the unsharded, de-quantised set
             whole = rir.Database.from_descriptors(X.to(dev), dtype)
             Xf = whole.rows.cpu()

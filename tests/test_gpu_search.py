@@ -435,3 +435,22 @@ def test_descriptor_store_to_sharded_search(cuda_device, tmp_path):
     res = [p.search(qr, qs, k) for p in parts]
     ms, mi = rir.merge_topk(torch.stack([r[0] for r in res]), torch.stack([r[1] for r in res]))
     assert torch.equal(mi, want_ix) and torch.equal(ms, want_sc)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp8", "fp32"])
+def test_query_host_single_call(cuda_device, dtype):
+    """rir_search_host: host fp32 queries in, host top-k out, one C-ABI call == pack + search + copies by hand."""
+    nq, n, d, k = 9, 80000, 128, 30
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=55)
+    db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    want_sc, want_ix = db.search(qr, qs, k)
+    qh = Q.contiguous().pin_memory()
+    sc, ix = db.query_host(qh, k)
+    assert sc.device.type == "cpu" and ix.dtype == torch.int32
+    assert torch.equal(ix, want_ix.cpu()) and torch.equal(sc, want_sc.cpu())
+    out = (torch.empty(nq, k).pin_memory(), torch.empty(nq, k, dtype=torch.int32).pin_memory())
+    sc2, ix2 = db.query_host(qh, k, out=out)      # result buffers re-used
+    assert sc2 is out[0] and torch.equal(ix2, want_ix.cpu())
+    with pytest.raises(TypeError):
+        db.query_host(Q.to(cuda_device), k)
