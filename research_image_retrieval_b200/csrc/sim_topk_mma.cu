@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             uint32_t mask = 0u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) mask |= (sc[j] >= thr) ? (1u << j) : 0u;
+            if (g.debug & 32) mask &= (mask == 0x12345678u) ? ~0u : 0u;  // development: no insertions
 #pragma unroll 1
             while (mask) {
               const int j = __ffs(mask) - 1;
