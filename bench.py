@@ -342,13 +342,14 @@ def run_ours(args):
                                     else "1590 TFLOP/s (of fallback, B200_PROFILING.md)") +
                                    (" x2 for fp8" if args.dtype == "fp8" else "")}
 
-    # our kernels per step: fused tcgen05 path = scan, select, overflow fallback; stream path adds sample + threshold
+    # our kernels per step (memsets are not kernels): fused tcgen05 path = scan + select (which also redoes overflowed
+    # queries itself); the three-launch route adds sample + threshold; tiny shards: scan-all + select
     if n_local <= 16384:
         kernels_per_step = 2
-    elif stream_path:
-        kernels_per_step = 5
+    elif stream_path or n_local < 2 * 148 * 256 or args.k > 592:
+        kernels_per_step = 4
     else:
-        kernels_per_step = 3
+        kernels_per_step = 2
     kernels_per_step += 1 if world > 1 else 0  # merge
 
     if rank == 0:

@@ -84,7 +84,8 @@ struct MmaGeom {
   int fused;          // kModeFused
   int ra_rounds;      // fused: rounds [0, ra_rounds) are the sample phase
   int tile_n;         // database rows per tile: 256, or 128 when a small shard would leave the last round mostly idle
-  int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue math
+  int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue (timing
+                      // decomposition of mainloop vs epilogue; results are garbage)
 };
 
 enum { kShareNone = 0, kShareQ = 1, kShareX = 2 };
@@ -522,23 +523,15 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         }
         epi_bar();
       }
-      const long long dbg_t0 = (g.debug & 4) ? clock64() : 0;
       mbar_wait(&tail->tmem_full[ab], aph);
       tc_fence_after();
-      const long long dbg_t1 = (g.debug & 4) ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * kBufCols + mblk * kTileN);
       // 16 columns at a time, double buffered: the tcgen05.ld of the next unit is in flight while this one is
       // processed (TMEM loads take a few hundred clocks while the MMAs of the other accumulator are running).
       // Survivors are found with a per-lane bitmask — no divergent per-column branches (the unrolled 32-way version
       // of this code took ~27k clocks per tile, 10x the budget) — and each lane then walks ITS bits, fetching the
       // score from registers with a select tree, so the score array is never indexed dynamically.
-      uint32_t dbg_acc = 0u;
       auto process16 = [&](const uint32_t (&vv)[16], int c0) {
-        if (g.debug & 8) {  // development: TMEM loads only
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dbg_acc ^= vv[j];
-          return;
-        }
         float sc[16];
         if (p.x_scale) {
 #pragma unroll
@@ -560,7 +553,6 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             mask |= __hge2_mask(__floats2bfloat162_rn(sc[2 * j], sc[2 * j + 1]), ts2) & (0x00010001u << j);
           // qvalid: lanes of queries that do not exist hold whatever the (trimmed) query box left in shared memory
           if (!qvalid) mask = 0u;
-          if (g.debug & 16) mask &= (mask == 0x12345678u) ? ~0u : 0u;  // development: no slow path
 #pragma unroll 1
           while (mask) {  // rare: ~k*n/S survivors per query over the whole scan
             const int b = __ffs(mask) - 1;
@@ -584,7 +576,6 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             uint32_t mask = 0u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) mask |= (sc[j] >= thr) ? (1u << j) : 0u;
-            if (g.debug & 32) mask &= (mask == 0x12345678u) ? ~0u : 0u;  // development: no insertions
 #pragma unroll 1
             while (mask) {
               const int j = __ffs(mask) - 1;
@@ -644,10 +635,6 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[ab]), 0));  // the leader's MMA thread waits
         else mbar_arrive(&tail->tmem_empty[ab]);
       }
-      if ((g.debug & 8) && dbg_acc == 0x9e3779b9u) p.tau_idx[0] = dbg_acc;  // keeps the loads alive
-      if ((g.debug & 4) && blockIdx.x < 2 && lane == 0 && rd < 6)
-        printf("dbg cta %d warp %d rd %lld: wait %lld clk, columns %lld clk\n", (int)blockIdx.x, warp, rd,
-               dbg_t1 - dbg_t0, clock64() - dbg_t1);
       if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
       if (mode == kModeSample && p.topt > 0 && qvalid) {  // slot = (query, sample tile): every slot is written
 #pragma unroll
