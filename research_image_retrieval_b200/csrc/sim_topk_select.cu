@@ -67,38 +67,31 @@ int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_
 // ---------------------------------------------------------------------------------------------
 // CUDA-core dot products (fallback / redo / rescore paths): one warp per row, fp32 FMA
 // ---------------------------------------------------------------------------------------------
+// acc += <16 bytes of a row, matching 16-byte chunk c of the fp32 query in shared memory>, fixed FMA order
 template <int DT>
-__device__ __forceinline__ float dot_row(const uint8_t* row, const float* qs, int chunks, int lane);
+__device__ __forceinline__ float chunk_fma(const uint4& v, const float* qs, int c, float acc);
 
 template <>
-__device__ __forceinline__ float dot_row<RIR_BF16>(const uint8_t* row, const float* qs, int chunks, int lane) {
-  float acc = 0.f;
-  for (int c = lane; c < chunks; c += 32) {
-    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
-    const float4 q0 = reinterpret_cast<const float4*>(qs)[2 * c], q1 = reinterpret_cast<const float4*>(qs)[2 * c + 1];
-    acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
-    acc = fmaf(__uint_as_float(v.x & 0xffff0000u), q0.y, acc);
-    acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
-    acc = fmaf(__uint_as_float(v.y & 0xffff0000u), q0.w, acc);
-    acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
-    acc = fmaf(__uint_as_float(v.z & 0xffff0000u), q1.y, acc);
-    acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
-    acc = fmaf(__uint_as_float(v.w & 0xffff0000u), q1.w, acc);
-  }
-  return warp_sum(acc);
+__device__ __forceinline__ float chunk_fma<RIR_BF16>(const uint4& v, const float* qs, int c, float acc) {
+  const float4 q0 = reinterpret_cast<const float4*>(qs)[2 * c], q1 = reinterpret_cast<const float4*>(qs)[2 * c + 1];
+  acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
+  acc = fmaf(__uint_as_float(v.x & 0xffff0000u), q0.y, acc);
+  acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
+  acc = fmaf(__uint_as_float(v.y & 0xffff0000u), q0.w, acc);
+  acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
+  acc = fmaf(__uint_as_float(v.z & 0xffff0000u), q1.y, acc);
+  acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
+  acc = fmaf(__uint_as_float(v.w & 0xffff0000u), q1.w, acc);
+  return acc;
 }
 template <>
-__device__ __forceinline__ float dot_row<RIR_F32>(const uint8_t* row, const float* qs, int chunks, int lane) {
-  float acc = 0.f;
-  for (int c = lane; c < chunks; c += 32) {
-    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
-    const float4 q0 = reinterpret_cast<const float4*>(qs)[c];
-    acc = fmaf(__uint_as_float(v.x), q0.x, acc);
-    acc = fmaf(__uint_as_float(v.y), q0.y, acc);
-    acc = fmaf(__uint_as_float(v.z), q0.z, acc);
-    acc = fmaf(__uint_as_float(v.w), q0.w, acc);
-  }
-  return warp_sum(acc);
+__device__ __forceinline__ float chunk_fma<RIR_F32>(const uint4& v, const float* qs, int c, float acc) {
+  const float4 q0 = reinterpret_cast<const float4*>(qs)[c];
+  acc = fmaf(__uint_as_float(v.x), q0.x, acc);
+  acc = fmaf(__uint_as_float(v.y), q0.y, acc);
+  acc = fmaf(__uint_as_float(v.z), q0.z, acc);
+  acc = fmaf(__uint_as_float(v.w), q0.w, acc);
+  return acc;
 }
 __device__ __forceinline__ void fp8x4_to_float(uint32_t w, float* f) {
   const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w & 0xffffu), __NV_E4M3);
@@ -108,19 +101,39 @@ __device__ __forceinline__ void fp8x4_to_float(uint32_t w, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 template <>
-__device__ __forceinline__ float dot_row<RIR_FP8E4M3>(const uint8_t* row, const float* qs, int chunks, int lane) {
-  float acc = 0.f;
-  for (int c = lane; c < chunks; c += 32) {
-    const uint4 v = ldg_stream_16B(row + (size_t)c * 16);
-    const float* qp = qs + (size_t)c * 16;
-    float f[16];
-    fp8x4_to_float(v.x, f); fp8x4_to_float(v.y, f + 4); fp8x4_to_float(v.z, f + 8); fp8x4_to_float(v.w, f + 12);
+__device__ __forceinline__ float chunk_fma<RIR_FP8E4M3>(const uint4& v, const float* qs, int c, float acc) {
+  const float* qp = qs + (size_t)c * 16;
+  float f[16];
+  fp8x4_to_float(v.x, f); fp8x4_to_float(v.y, f + 4); fp8x4_to_float(v.z, f + 8); fp8x4_to_float(v.w, f + 12);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) acc = fmaf(f[e], qp[e], acc);
-  }
+  for (int e = 0; e < 16; ++e) acc = fmaf(f[e], qp[e], acc);
+  return acc;
+}
+
+template <int DT>
+__device__ __forceinline__ float dot_row(const uint8_t* row, const float* qs, int chunks, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < chunks; c += 32) acc = chunk_fma<DT>(ldg_stream_16B(row + (size_t)c * 16), qs, c, acc);
   return warp_sum(acc);
 }
 
+// Four consecutive rows at once: the four rows' loads of a chunk are independent, so four times as many bytes are
+// in flight per warp (these paths are latency-bound).  Per row the arithmetic (and its order) is dot_row's.
+template <int DT>
+__device__ __forceinline__ void dot_rows4(const uint8_t* row0, size_t stride, int nvalid, const float* qs, int chunks,
+                                          int lane, float (&out)[4]) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane; c < chunks; c += 32) {
+    uint4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      v[r] = r < nvalid ? ldg_stream_16B(row0 + (size_t)r * stride + (size_t)c * 16) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = chunk_fma<DT>(v[r], qs, c, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) out[r] = warp_sum(acc[r]);
+}
 
 // query row q -> fp32 shared memory (q_scale folded in)
 template <int DT>
@@ -206,14 +219,21 @@ __device__ void exact_scan_body(const SimParams& p, int q, int k, int bufcap, ui
   const int chunks = p.row_bytes >> 4;
   for (long long base = 0; base < p.n; base += rows_per_iter) {
     const unsigned long long t = tau;
+    {
+      const long long b4 = base + warp * 4;
+      const int nvalid = b4 >= p.n ? 0 : (int)((p.n - b4) < 4 ? (p.n - b4) : 4);
+      if (nvalid > 0) {
+        float sc4[4];
+        dot_rows4<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)b4 * p.row_bytes, (size_t)p.row_bytes, nvalid, qs,
+                      chunks, lane, sc4);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const long long row = base + warp * 4 + r;
-      if (row < p.n) {
-        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
-        if (p.x_scale) s *= p.x_scale[row];
-        const unsigned long long key = make_key(s, (uint32_t)row);
-        if (lane == 0 && key > t) buf[atomicAdd(&count, 1)] = key;
+        for (int r = 0; r < 4; ++r) {
+          if (r >= nvalid) continue;
+          float s = sc4[r];
+          if (p.x_scale) s *= p.x_scale[b4 + r];
+          const unsigned long long key = make_key(s, (uint32_t)(b4 + r));
+          if (lane == 0 && key > t) buf[atomicAdd(&count, 1)] = key;
+        }
       }
     }
     __syncthreads();
@@ -277,15 +297,25 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
     const float ts_lo = ts - 1e-4f * (fabsf(ts) + 1e-2f);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int chunks = p.row_bytes >> 4;
-    for (int r = 0; r < nredo; ++r) {
-      const long long tile = ((long long)s_redo[r] * p.perm_mul) % p.perm_n;
+    for (int ri = 0; ri < nredo; ++ri) {
+      const long long tile = ((long long)s_redo[ri] * p.perm_mul) % p.perm_n;
       const long long row0 = tile * p.tile_rows;
-      for (long long row = row0 + warp; row < row0 + p.tile_rows && row < p.n; row += nwarps) {
-        float s = dot_row<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)row * p.row_bytes, qs, chunks, lane);
-        if (p.x_scale) s *= p.x_scale[row];
-        if (lane == 0 && s >= ts_lo) {
-          const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
-          if (pos < (uint32_t)p.cap) c[pos] = make_key(s, (uint32_t)row);
+      long long end = row0 + p.tile_rows;
+      if (end > p.n) end = p.n;
+      for (long long base = row0 + warp * 4; base < end; base += (long long)nwarps * 4) {
+        const int nvalid = (int)((end - base) < 4 ? (end - base) : 4);
+        float sc4[4];
+        dot_rows4<DT>(reinterpret_cast<const uint8_t*>(p.X) + (size_t)base * p.row_bytes, (size_t)p.row_bytes, nvalid, qs,
+                      chunks, lane, sc4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r >= nvalid) continue;
+          float s = sc4[r];
+          if (p.x_scale) s *= p.x_scale[base + r];
+          if (lane == 0 && s >= ts_lo) {
+            const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
+            if (pos < (uint32_t)p.cap) c[pos] = make_key(s, (uint32_t)(base + r));
+          }
         }
       }
     }
