@@ -454,3 +454,60 @@ def test_query_host_single_call(cuda_device, dtype):
     assert sc2 is out[0] and torch.equal(ix2, want_ix.cpu())
     with pytest.raises(TypeError):
         db.query_host(Q.to(cuda_device), k)
+
+
+def test_clustered_database_r1m_layout(cuda_device):
+    """R1M-style layout: the landmark images (every query's positives, contiguous per landmark) lead the database,
+    distractors follow.  Tile 0 — always a first-phase tile of the fused scan — then holds ~80 rows per query that beat
+    every distractor, far more than the 8 keys kept per tile: the select kernel must re-score it (and the tiles the
+    permutation happens to pick).  Result must still be exact."""
+    nq, per, n, d, k = 24, 80, 300000, 128, 100
+    gen = torch.Generator(device=cuda_device).manual_seed(77)
+    X = _unit_rows_gpu(n, d, gen, cuda_device)
+    Q = _unit_rows_gpu(nq, d, gen, cuda_device)
+    for i in range(nq):  # cluster i: rows [i*per, (i+1)*per)
+        rows = Q[i][None] + torch.randn(per, d, generator=gen, device=cuda_device) * (0.6 / d ** 0.5)
+        X[i * per:(i + 1) * per] = rows / rows.norm(dim=1, keepdim=True)
+    db = rir.Database.from_descriptors(X, "bf16")
+    qr, qs = db.pack_queries(Q)
+    sc, ix = db.search(qr, qs, k, path="mma")
+    ixl = ix.long()
+    for i in range(nq):
+        inside = ((ixl[i] >= i * per) & (ixl[i] < (i + 1) * per)).sum().item()
+        assert inside == per, f"query {i}: only {inside} of its {per} cluster rows came back"
+    assert bool((sc[:, 1:] <= sc[:, :-1]).all())
+    Xb, Qb = db.rows.float(), qr.float()
+    rescored = torch.einsum("qkd,qd->qk", Xb[ixl], Qb)
+    assert torch.allclose(sc, rescored, rtol=2e-4, atol=2e-6)
+    _nothing_better_outside(Qb, db.rows, sc, ixl, 1e-3)
+    sc_e, ix_e = db.search(qr[:3].contiguous(), None, k, path="exact")   # independent implementation
+    ok, msg = S.indices_match_up_to_ties(ix[:3].cpu().numpy().astype(np.int64), sc[:3].cpu().numpy(),
+                                         ix_e.cpu().numpy().astype(np.int64), sc_e.cpu().numpy(), 1e-3)
+    assert ok, msg
+
+
+BOUNDARY_CASES = [
+    # nq, n, d, k, dtype — mode / tile / block boundaries of the tcgen05 path
+    (128, 75776, 64, 10, "bf16"),     # exactly one full query block; n == 2 * 148 tiles exactly (smallest fused shard)
+    (129, 75775, 64, 10, "bf16"),     # one row short of the fused route (three-launch route), two query blocks
+    (256, 80000, 64, 7, "bf16"),      # two full blocks -> one CTA pair
+    (257, 80001, 64, 7, "fp8"),       # third block with a single query, n % 256 == 129
+    (1, 76000, 2048, 1, "bf16"),      # k = 1, one query, full-width rows
+    (3, 76000, 64, 592, "bf16"),      # largest k of the fused route (148 * 8 >= 2k)
+    (3, 76000, 64, 593, "bf16"),      # first k of the three-launch route
+    (2, 40000, 64, 4096, "bf16"),     # large k: dense sample, separate exact fallback kernel route
+    (70, 80000, 4096, 20, "bf16"),    # 8 KB rows: 64 K-chunks per tile
+    (16, 77000, 16, 5, "fp8"),        # a single 16-byte chunk per row
+]
+
+
+@pytest.mark.parametrize("nq,n,d,k,dtype", BOUNDARY_CASES)
+def test_tensor_path_boundaries(cuda_device, nq, n, d, k, dtype):
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=7 * n + nq + k, n_pos=min(4, k))
+    db = rir.Database.from_descriptors(X.to(cuda_device), dtype)
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k, path="mma")
+    torch.cuda.synchronize()
+    Xf = _dequant(db.rows, db.scale, dtype)[:, :d]
+    Qf = _dequant(qr, qs, dtype)[:, :d]
+    _check(sc, ix, Qf, Xf, k, 1e-3)
