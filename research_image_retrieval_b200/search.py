@@ -319,7 +319,9 @@ class ShardedDatabase:
     # ---- NVLink peer-memory exchange -----------------------------------------------------------
     def enable_peer_exchange(self, nq_max: int, k_max: int) -> bool:
         """Collective.  Allocates this rank's inbox, exchanges CUDA IPC handles through the process group and maps the
-        peers' inboxes.  Returns False (and leaves the all-gather path in place) for a single rank."""
+        peers' inboxes.  Returns False — on EVERY rank, leaving the all-gather path in place — for a single rank or
+        when any rank cannot allocate / export / map (no peer access, IPC unavailable); never raises half-way through a
+        collective."""
         import ctypes
 
         import torch.distributed as dist
@@ -329,27 +331,44 @@ class ShardedDatabase:
             raise ValueError("peer exchange supports at most 16 ranks")
         lib = _lib.load()
         dev = self.local.rows.device
+        ptr, handle, err = ctypes.c_void_p(), ctypes.create_string_buffer(64), None
         with torch.cuda.device(dev):
-            nbytes = lib.rir_exchange_bytes(self.world, int(nq_max), int(k_max))
-            if nbytes == 0:
-                raise ValueError("bad exchange shape")
-            ptr = ctypes.c_void_p()
-            _lib.check(lib.rir_peer_alloc(nbytes, ctypes.byref(ptr)))
-            handle = ctypes.create_string_buffer(64)
-            _lib.check(lib.rir_peer_export(ptr, handle))
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
-            peers = (ctypes.c_void_p * self.world)()
-            for g, h in enumerate(handles):
-                if g == self.rank:
-                    peers[g] = ptr.value
-                else:
-                    q = ctypes.c_void_p()
-                    _lib.check(lib.rir_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
-                    peers[g] = q.value
-                    self._opened.append(q)
-            dist.barrier(group=self.group)  # every inbox is mapped (and zeroed) before the first store into it
-        self._inbox, self._peers = ptr, peers
+            try:
+                nbytes = lib.rir_exchange_bytes(self.world, int(nq_max), int(k_max))
+                if nbytes == 0:
+                    raise ValueError("bad exchange shape")
+                _lib.check(lib.rir_peer_alloc(nbytes, ctypes.byref(ptr)))
+                _lib.check(lib.rir_peer_export(ptr, handle))
+            except Exception as e:  # reported to every rank below
+                err = str(e)
+            infos = [None] * self.world
+            dist.all_gather_object(infos, (err, bytes(handle.raw)), group=self.group)
+            opened, peers = [], (ctypes.c_void_p * self.world)()
+            if all(i[0] is None for i in infos):
+                try:
+                    for g, (_, h) in enumerate(infos):
+                        if g == self.rank:
+                            peers[g] = ptr.value
+                        else:
+                            q = ctypes.c_void_p()
+                            _lib.check(lib.rir_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q)))
+                            peers[g] = q.value
+                            opened.append(q)
+                except Exception as e:
+                    err = str(e)
+            else:
+                err = err or "a peer could not allocate its inbox"
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=self.group)  # also: every inbox is mapped and zeroed
+            if not all(oks):
+                for q in opened:
+                    lib.rir_peer_close(q)
+                dist.barrier(group=self.group)
+                if ptr.value:
+                    lib.rir_peer_free(ptr)
+                self.peer_exchange_error = err or "a peer could not map the inboxes"
+                return False
+        self._inbox, self._peers, self._opened = ptr, peers, opened
         self._nq_max, self._k_max, self._epoch = int(nq_max), int(k_max), 0
         return True
 

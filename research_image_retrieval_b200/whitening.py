@@ -58,13 +58,17 @@ class ConvDimReduction(nn.Conv2d):
         super().__init__(input_dim, dim, (1, 1), padding=0, bias=True)
 
     def initialize_pca_whitening(self, des):
-        """des [N, input_dim].  Sets weight = P[:dim], bias = -(P m)[:dim]; returns (m.T, P.T) like the reference."""
-        m, P = pcawhitenlearn_shrinkage(des, device=self.weight.device if self.weight.is_cuda else None)
-        m, P = m.T, P.T
-        projection = torch.Tensor(P[:self.weight.shape[0], :]).unsqueeze(-1).unsqueeze(-1)
-        self.weight.data = projection.to(self.weight.device)
-        self.weight.requires_grad = False
-        projected_shift = -torch.mm(torch.FloatTensor(P), torch.FloatTensor(m)).squeeze()
-        self.bias.data = projected_shift[:self.weight.shape[0]].to(self.bias.device)
-        self.bias.requires_grad = False
-        return m.T, P.T
+        """des [N, input_dim] descriptors.  Fills the layer with the first `dim` whitening directions,
+        weight = P[:dim] and bias = -(P m)[:dim], freezes both, and returns `(m, P.T)` exactly as
+        pcawhitenlearn_shrinkage does (the reference's method returns the same pair, networks/spca.py:215-227)."""
+        dev = self.weight.device if self.weight.is_cuda else None
+        m, Pt = pcawhitenlearn_shrinkage(des, device=dev)
+        dim = self.out_channels
+        rows = torch.from_numpy(np.ascontiguousarray(Pt.T[:dim])).float()          # [dim, input_dim]
+        shift = -(rows @ torch.from_numpy(np.ascontiguousarray(m.reshape(-1))).float())
+        with torch.no_grad():
+            self.weight.copy_(rows.reshape(dim, -1, 1, 1).to(self.weight.device))
+            self.bias.copy_(shift.to(self.bias.device))
+        self.weight.requires_grad_(False)
+        self.bias.requires_grad_(False)
+        return m, Pt

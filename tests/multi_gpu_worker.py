@@ -29,8 +29,9 @@ def main():
         (3, 50000, 128, 10, "bf16"),
         (9, 150, 64, 100, "fp32"),        # shards shorter than k: padded lists
         (130, 90000, 64, 20, "fp8"),
+        (5000, 80000, 64, 10, "bf16"),    # more than one internal query group (4096) through the exchange
     ]
-    nq_max, k_max = 130, 100
+    nq_max, k_max = 5000, 100
     first = None
     for ci, (nq, n, d, k, dtype) in enumerate(cases):
         Q, X, _ = synth.retrieval_set(nq, n, d, seed=100 + ci)
