@@ -31,18 +31,19 @@ PROTO_HARD = 0x52              # ok = hard(B)        junk = junk(C) | easy(A)   
 def ids_to_csr(lists):
     """[array-like of ids per query] -> (ids int32 sorted within each query, off int32[nq+1]).
 
-    Duplicates are kept: the reference uses len(ok) (duplicates included) as the number of positives."""
-    off = np.zeros(len(lists) + 1, dtype=np.int32)
-    parts = []
-    for i, l in enumerate(lists):
-        a = np.asarray(l).reshape(-1)
-        if a.size and not np.issubdtype(a.dtype, np.integer):
-            a = a.astype(np.int64)
-        a = np.sort(a.astype(np.int32, copy=False)) if a.size else np.empty(0, dtype=np.int32)
-        parts.append(a)
-        off[i + 1] = off[i] + a.size
-    ids = np.concatenate(parts) if parts else np.empty(0, dtype=np.int32)
-    return np.ascontiguousarray(ids, dtype=np.int32), off
+    Duplicates are kept: the reference uses len(ok) (duplicates included) as the number of positives.
+    One concatenate + one lexsort for the whole query set (no per-query numpy calls)."""
+    nq = len(lists)
+    arrs = [np.asarray(l).reshape(-1) for l in lists]
+    lens = np.fromiter((a.size for a in arrs), dtype=np.int64, count=nq)
+    off = np.zeros(nq + 1, dtype=np.int32)
+    np.cumsum(lens, out=off[1:])
+    if int(off[-1]) == 0:
+        return np.empty(0, dtype=np.int32), off
+    flat = np.concatenate([a.astype(np.int64, copy=False) for a in arrs if a.size])
+    owner = np.repeat(np.arange(nq, dtype=np.int64), lens)
+    order = np.lexsort((flat, owner))            # by query, then by id
+    return np.ascontiguousarray(flat[order], dtype=np.int32), off
 
 
 def ranks_to_rows(ranks, li: bool, nq: int):
@@ -64,7 +65,7 @@ def ranks_to_rows(ranks, li: bool, nq: int):
     r = np.asarray(ranks)
     if r.ndim != 2:
         raise ValueError("ranks must be 2-D [L, nq]")
-    return np.ascontiguousarray(r.T.astype(np.int32)), r.shape[0]
+    return np.ascontiguousarray(r.T, dtype=np.int32), r.shape[0]  # one transposing + narrowing pass
 
 
 def _dev(a, device):
@@ -74,41 +75,51 @@ def _dev(a, device):
 
 
 def _run_map(rows, L, nq, lists_abc, protos, keeps, device=None):
-    """Launch rir_compute_map; returns host numpy (map[P], aps[P,nq], mpr[P,nk], prs[P,nq,nk], status[P,nq])."""
+    """Launch rir_compute_map; returns host numpy (map[P], aps[P,nq], mpr[P,nk], prs[P,nq,nk], status[P,nq]).
+
+    Two host->device copies (ranked lists; all id lists + offsets packed into one int32 array) and ONE device->host
+    copy (every output carved out of one buffer): at ROxford size the copies and their synchronisations, not the
+    kernel, are the cost."""
     lib = _lib.load()
     if device is None:
         device = rows.device if isinstance(rows, torch.Tensor) and rows.is_cuda else torch.device("cuda", torch.cuda.current_device())
     rows_d = _dev(rows, device)
     ld = rows_d.shape[1]
-    ptrs = []
-    keepalive = []
+    # pack [ids_A | off_A | ids_B | off_B | ids_C | off_C] (absent lists contribute nothing)
+    pieces, where, pos = [], [], 0
     for lst in lists_abc:
         if lst is None:
-            ptrs += [None, None]
+            where.append(None)
             continue
         ids, off = lst
-        ids_d = _dev(ids if ids.size else np.zeros(1, dtype=np.int32), device)
-        off_d = _dev(off, device)
-        keepalive += [ids_d, off_d]
-        ptrs += [ids_d.data_ptr(), off_d.data_ptr()]
+        ids = ids if ids.size else np.zeros(1, dtype=np.int32)
+        where.append((pos, pos + ids.size))
+        pieces += [np.ascontiguousarray(ids, dtype=np.int32), np.ascontiguousarray(off, dtype=np.int32)]
+        pos += ids.size + off.size
+    meta_d = _dev(np.concatenate(pieces) if pieces else np.zeros(1, dtype=np.int32), device)
+    ptrs = []
+    for w in where:
+        ptrs += [None, None] if w is None else [meta_d.data_ptr() + 4 * w[0], meta_d.data_ptr() + 4 * w[1]]
     P = len(protos)
     keeps = list(keeps) if keeps else []
     nk = len(keeps)
-    out_map = torch.empty(P, dtype=torch.float64, device=device)
-    out_aps = torch.empty((P, nq), dtype=torch.float64, device=device)
-    out_mpr = torch.empty((P, max(nk, 1)), dtype=torch.float64, device=device)
-    out_prs = torch.empty((P, nq, max(nk, 1)), dtype=torch.float64, device=device)
-    out_status = torch.empty((P, nq), dtype=torch.int32, device=device)
+    nk1 = max(nk, 1)
+    n_f64 = P + P * nq + P * nk1 + P * nq * nk1
+    out = torch.empty(n_f64 * 8 + P * nq * 4, dtype=torch.uint8, device=device)   # fp64 block, then int32 status
+    base = out.data_ptr()
+    o_map, o_aps, o_mpr, o_prs = 0, P, P + P * nq, P + P * nq + P * nk1
     proto_arr = (ctypes.c_int32 * P)(*protos)
-    kappa_arr = (ctypes.c_int32 * max(nk, 1))(*([int(k) for k in keeps] or [0]))
+    kappa_arr = (ctypes.c_int32 * nk1)(*([int(k) for k in keeps] or [0]))
     with torch.cuda.device(device):
         _lib.check(lib.rir_compute_map(rows_d.data_ptr(), nq, int(L), int(ld), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
-                                       ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk, out_map.data_ptr(),
-                                       out_aps.data_ptr(), out_mpr.data_ptr(), out_prs.data_ptr(),
-                                       out_status.data_ptr(), _lib.stream_ptr()))
-    res = (out_map.cpu().numpy(), out_aps.cpu().numpy(), out_mpr.cpu().numpy()[:, :nk],
-           out_prs.cpu().numpy()[:, :, :nk], out_status.cpu().numpy())
-    del keepalive
+                                       ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk, base + 8 * o_map, base + 8 * o_aps,
+                                       base + 8 * o_mpr, base + 8 * o_prs, base + 8 * n_f64, _lib.stream_ptr()))
+    host = out.cpu().numpy()
+    f64 = host[: n_f64 * 8].view(np.float64)
+    status = host[n_f64 * 8:].view(np.int32).reshape(P, nq)
+    res = (f64[o_map:o_aps].copy(), f64[o_aps:o_mpr].reshape(P, nq).copy(),
+           f64[o_mpr:o_prs].reshape(P, nk1)[:, :nk].copy(), f64[o_prs:].reshape(P, nq, nk1)[:, :, :nk].copy(), status.copy())
+    del meta_d, rows_d
     return res
 
 
