@@ -230,6 +230,18 @@ __device__ __forceinline__ void tma_tensor2d_g2s_2sm(void* dst_smem, const void*
       "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// same, multicast: the box lands at the same offset of every CTA in cta_mask; with cta_group::2 the completion is
+// signalled, for each destination CTA, on the CTA of ITS pair that has the parity of the mbarrier's owner (pass the
+// address inside the executing CTA's pair leader -> every destination pair's leader is signalled)
+__device__ __forceinline__ void tma_tensor2d_g2s_2sm_mcast(void* dst_smem, const void* tmap, int32_t c0, int32_t c1,
+                                                           uint32_t bar_cluster_addr, uint16_t cta_mask,
+                                                           uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(bar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)

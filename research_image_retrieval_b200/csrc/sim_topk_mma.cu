@@ -76,7 +76,8 @@ struct MmaGeom {
   uint32_t idesc;     // tcgen05 instruction descriptor
   int x_streamed_once;
   int na, nb;         // ring depths (query chunks / database chunks)
-  int csize;          // cluster size: 1 or 2
+  int csize;          // cluster size: 1, 2 or 4
+  int npairs;         // CTA pairs per cluster (cta_group::2 only): 1, or 2 = two pairs that multicast the query chunk
   int share;          // 0 none, 1 query chunk shared (CTAs differ in tile), 2 database chunk shared (differ in super-block)
   int nqg;            // super-block groups = ceil(nsb / csize) when share == 2, else nsb
   long long rounds;   // persistent-loop trips, identical for every CTA (dummy items keep clusters in lock step)
@@ -98,8 +99,10 @@ __device__ __forceinline__ void item_of(const MmaGeom& g, long long rd, int clus
     *v = j * g.csize + crank;
     *sb = 0;
   } else if (g.share == kShareX) {
-    *v = j / g.nqg;
-    *sb = (int)(j % g.nqg) * g.csize + crank;
+    // clusters of 2: the two CTAs take the same tile and neighbouring super-blocks.  CTA pairs in clusters of 4
+    // (g.npairs == 2): pair p = crank >> 1 takes tile 2*tp + p, the CTAs of a pair take super-blocks 2*qg + (crank & 1)
+    *v = (j / g.nqg) * g.npairs + (crank >> 1) * (g.npairs - 1);
+    *sb = (int)(j % g.nqg) * (g.csize / g.npairs) + (g.npairs > 1 ? (crank & 1) : crank);
   } else {
     *v = j / g.nsb;
     *sb = (int)(j % g.nsb);
@@ -248,7 +251,13 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   const int cb = (!TWO && g.share == kShareX) ? g.csize : 1;  // CTAs sharing one database chunk (multicast)
   // CTA pair (TWO): the leader (cluster rank 0) issues every MMA for both SMs; both CTAs' TMA loads complete on the
   // LEADER's full barriers; tcgen05.commit releases ring slots / publishes accumulators in both CTAs.
-  const bool leader = !TWO || crank == 0;
+  // In clusters of 4 two pairs (ranks {0,1} and {2,3}) work on neighbouring tiles with the SAME queries: each CTA
+  // loads half of its query block and multicasts it to the CTA of the same parity in the other pair.
+  const int pr = crank & 1;                          // rank inside the pair
+  const int pi = crank >> 1;                         // pair inside the cluster
+  const bool leader = !TWO || pr == 0;
+  const uint32_t leader_rank = (uint32_t)(crank & ~1);
+  const uint16_t pair_mask = (uint16_t)(0x3u << (2 * pi));
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) {  // SWIZZLE_128B tiles need 1024-byte aligned shared memory
@@ -257,7 +266,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     }
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(&tail->full_a[s], 1);
-      mbar_init(&tail->empty_a[s], ca);  // a shared slot is free once all sharers' MMAs have read it
+      // a shared slot is free once all sharers' MMAs have read it (pairs sharing the query chunk: one commit per pair)
+      mbar_init(&tail->empty_a[s], TWO ? g.npairs : ca);
       mbar_init(&tail->full_b[s], 1);
       mbar_init(&tail->empty_b[s], cb);
     }
@@ -314,8 +324,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           uint8_t* dst = ring_b + (size_t)s * kBSlot;
           if (TWO) {  // my 128 rows into my shared memory; both halves complete on the leader's barrier
             if (leader) mbar_expect_tx(&tail->full_b[s], b_bytes);
-            tma_tensor2d_g2s_2sm(dst, &tmX, kc * kElemsPerChunk, row0 + crank * (g.tile_n / 2),
-                                 mapa_u32(smem_u32(&tail->full_b[s]), 0), pol_x);
+            tma_tensor2d_g2s_2sm(dst, &tmX, kc * kElemsPerChunk, row0 + pr * (g.tile_n / 2),
+                                 mapa_u32(smem_u32(&tail->full_b[s]), leader_rank), pol_x);
           } else {
             mbar_expect_tx(&tail->full_b[s], b_bytes);
             if (cb == 1)
@@ -352,9 +362,13 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           for (int m = 0; m < MB; ++m) {
             uint8_t* dst = ring_a + (size_t)s * kASlot + (size_t)m * kABytes;
             const int qrow0 = (sb * MB + m) * kTileM;
-            if (TWO)
-              tma_tensor2d_g2s_2sm(dst, &tmQ, kc * kElemsPerChunk, qrow0, mapa_u32(smem_u32(&tail->full_a[s]), 0),
-                                   pol_q);
+            if (TWO && g.npairs == 1)
+              tma_tensor2d_g2s_2sm(dst, &tmQ, kc * kElemsPerChunk, qrow0,
+                                   mapa_u32(smem_u32(&tail->full_a[s]), leader_rank), pol_q);
+            else if (TWO)  // my half of the block's rows, also delivered to the same-parity CTA of the other pair
+              tma_tensor2d_g2s_2sm_mcast(dst + (size_t)pi * (kABytes / 2), &tmQ, kc * kElemsPerChunk,
+                                         qrow0 + pi * (kTileM / 2), mapa_u32(smem_u32(&tail->full_a[s]), leader_rank),
+                                         (uint16_t)((1u << pr) | (1u << (pr + 2))), pol_q);
             else if (ca == 1)
               tma_tensor2d_g2s(dst, &tmQ, kc * kElemsPerChunk, qrow0, &tail->full_a[s], pol_q);
             else
@@ -401,8 +415,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           }
           // both slots are free once these MMAs have read them; a shared slot is released in every sharer
           if (TWO) {
-            umma_commit_2sm(&tail->empty_a[sa], cmask);
-            umma_commit_2sm(&tail->empty_b[sb_], cmask);
+            umma_commit_2sm(&tail->empty_a[sa], cmask);       // every CTA that wrote into / shares this slot
+            umma_commit_2sm(&tail->empty_b[sb_], pair_mask);  // database halves are private to the pair
           } else {
             if (ca == 1) umma_commit(&tail->empty_a[sa]); else umma_commit_mcast(&tail->empty_a[sa], cmask);
             if (cb == 1) umma_commit(&tail->empty_b[sb_]); else umma_commit_mcast(&tail->empty_b[sb_], cmask);
@@ -411,7 +425,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           if (++sb_ == g.nb) { sb_ = 0; phb ^= 1u; }
         }
         // accumulators complete -> epilogue (of both CTAs of a pair)
-        if (TWO) umma_commit_2sm(&tail->tmem_full[ab], cmask); else umma_commit(&tail->tmem_full[ab]);
+        if (TWO) umma_commit_2sm(&tail->tmem_full[ab], pair_mask); else umma_commit(&tail->tmem_full[ab]);
         if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
       }
     }
@@ -632,7 +646,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[ab]), 0));  // the leader's MMA thread waits
+        if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[ab]), leader_rank));  // my pair's MMA thread
         else mbar_arrive(&tail->tmem_empty[ab]);
       }
       if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
@@ -744,15 +758,6 @@ static long long gcd_ll(long long a, long long b) {
   return a;
 }
 
-bool mma_can_fuse(int nq, long long n, int k) {
-  (void)nq;
-  if (env_int("RIR_MMA_FUSED", 1) == 0) return false;
-  const int sms = sm_count();
-  const long long ntiles = (n + kTileN - 1) / kTileN;
-  // the first phase (one tile per CTA and query) must hold >= 2k keys and be a small part of the scan
-  return (long long)sms * kFusedTopT >= 2ll * k && sms * kFusedTopT <= kMaxFusedKeys && ntiles >= 2ll * sms;
-}
-
 template <int DT, int MB, int TWO>
 static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
                         unsigned grid, cudaStream_t st) {
@@ -784,6 +789,90 @@ static int launch_mma_d(const SimParams& p, const MmaGeom& g, const CUtensorMap&
   return mb == 1 ? launch_mma_t<DT, 1, 0>(p, g, tmQ, tmX, grid, st) : launch_mma_t<DT, 2, 0>(p, g, tmQ, tmX, grid, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch shape: blocks per CTA, CTA pairs, cluster size — shared by the planner (mma_can_fuse) and the launcher
+// ---------------------------------------------------------------------------------------------
+struct MmaShape {
+  int nqb, mb, nsb;
+  int csize, npairs, share, two;
+  int na, nb;
+  int max_ctas;  // CTAs that can be co-resident with this shape (the grid of a full launch)
+};
+
+template <int MB>
+static int max_active_clusters4() {  // clusters of 4 CTAs of the pair kernel that fit on the device at once
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  const int nslots = MB == 1 ? 6 : 4;
+  const size_t smem_bytes = (size_t)nslots * (kBBytes / 2) + (size_t)nslots * kABytes * MB + sizeof(MmaSmemTail);
+  auto kern = sim_mma_kernel<RIR_BF16, MB, 1>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(128 + 128 * MB);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  cudaGetLastError();
+  cached = n;
+  return cached;
+}
+
+static MmaShape plan_shape(int nq) {
+  const int sms = sm_count();
+  MmaShape h;
+  h.nqb = (nq + kTileM - 1) / kTileM;
+  // Measured on B200 (1M x 2048 bf16): CTA pair + one block per CTA (epilogue overlapped with the next tile's MMAs)
+  // 1220 TFLOP/s at 1024 queries; pair + two blocks per CTA 1110 (its epilogue is not overlapped); no pair 1074-1107.
+  h.mb = 1;
+  {
+    const int o = env_int("RIR_MMA_MB", 0);  // tuning override (development only)
+    if (o == 1 || o == 2) h.mb = o;
+  }
+  h.nsb = (h.nqb + h.mb - 1) / h.mb;
+  h.csize = cluster_size_for(sms);
+  h.npairs = 1;
+  h.share = h.csize == 1 ? kShareNone : (h.nsb == 1 ? kShareQ : kShareX);
+  // CTA pair (cta_group::2): the two CTAs of a pair work on the same database tile and different super-blocks;
+  // one M=256 MMA spans both SMs, each CTA stages only its 128 of the tile's 256 rows
+  h.two = (h.share == kShareX && env_int("RIR_MMA_TWO", 1) != 0) ? 1 : 0;
+  h.na = h.mb == 1 ? 4 : 3;  // ring depths: ~192 KB of shared memory either way
+  h.nb = h.mb == 1 ? 4 : 3;
+  h.max_ctas = sms - sms % h.csize;
+  if (h.two) {
+    h.na = h.nb = h.mb == 1 ? 6 : 4;
+    // Optional (RIR_MMA_CLUSTER4=1): two pairs per cluster that multicast the query chunk to each other.  Measured on
+    // B200 it halves the L2 reads of the query operand but is SLOWER overall (1024 queries: 1141 vs 1208 TFLOP/s;
+    // 4096: 1123 vs 1189): clusters of 4 cannot be placed on all 148 SMs (GPC sizes), and the mainloop turned out to be
+    // bound by the bytes each SM ingests (~33 B/clk), which multicast does not reduce.  Parity-tested, off by default.
+    const int want = env_int("RIR_MMA_CLUSTER4", 0);
+    const int n4 = want == 0 ? 0 : (h.mb == 1 ? max_active_clusters4<1>() : max_active_clusters4<2>());
+    if (want != 0 && n4 * 4 * 100 >= sms * 85) {
+      h.csize = 4;
+      h.npairs = 2;
+      h.max_ctas = n4 * 4 > sms ? sms - sms % 4 : n4 * 4;
+    }
+  }
+  return h;
+}
+
+bool mma_can_fuse(int nq, long long n, int k) {
+  if (env_int("RIR_MMA_FUSED", 1) == 0) return false;
+  const MmaShape h = plan_shape(nq);
+  const long long ntiles = (n + kTileN - 1) / kTileN;
+  // the first phase (one tile per CTA and query) must hold >= 2k keys and be a small part of the scan
+  return (long long)h.max_ctas * kFusedTopT >= 2ll * k && h.max_ctas * kFusedTopT <= kMaxFusedKeys &&
+         ntiles >= 2ll * h.max_ctas;
+}
+
 int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   if (dtype != RIR_BF16 && dtype != RIR_FP8E4M3) {
     set_error("sim_topk(mma): unsupported dtype %d", dtype);
@@ -794,16 +883,11 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     return RIR_E_ARG;
   }
   const int sms = sm_count();
+  const MmaShape h = plan_shape(p.nq);
+  const int mb = h.mb, two = h.two;
   MmaGeom g;
-  g.nqb = (p.nq + kTileM - 1) / kTileM;
-  // Measured on B200 (1M x 2048 bf16): CTA pair + one block per CTA (epilogue overlapped with the next tile's MMAs)
-  // 1220 TFLOP/s at 1024 queries; pair + two blocks per CTA 1110 (its epilogue is not overlapped); no pair 1074-1107.
-  int mb = 1;
-  {
-    const int o = env_int("RIR_MMA_MB", 0);  // tuning override (development only)
-    if (o == 1 || o == 2) mb = o;
-  }
-  g.nsb = (g.nqb + mb - 1) / mb;
+  g.nqb = h.nqb;
+  g.nsb = h.nsb;
   // Tile height: 256 rows.  128-row tiles were tried for small shards (8-way sharded cfg-2: 492 tiles / 148 CTAs =
   // 3.3 -> 4 rounds) to shorten the under-filled last round, but measured SLOWER (scan 0.121 vs 0.106 ms at 125,916
   // rows, 0.215 vs 0.172 ms at 251,831): the per-tile handshakes and epilogue outweigh the quantisation gain.
@@ -819,26 +903,21 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.tile_n >> 3) << 17) |
             ((uint32_t)(kTileM >> 4) << 24);
   g.x_streamed_once = (g.nsb == 1);
-  // ring depths: ~192 KB of shared memory either way
-  g.na = mb == 1 ? 4 : 3;
-  g.nb = mb == 1 ? 4 : 3;
-  g.csize = cluster_size_for(sms);
-  g.share = g.csize == 1 ? kShareNone : (g.nsb == 1 ? kShareQ : kShareX);
+  g.na = h.na;
+  g.nb = h.nb;
+  g.csize = h.csize;
+  g.npairs = h.npairs;
+  g.share = h.share;
   if (const char* e = getenv("RIR_MMA_RINGS")) {  // tuning override "na,nb" (development only)
     int a = 0, b = 0;
     if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a <= kMaxSlots && b <= kMaxSlots &&
-        (size_t)b * kBBytes + (size_t)a * kABytes * mb + sizeof(MmaSmemTail) <= 227 * 1024) {
+        (size_t)b * (two ? kBBytes / 2 : kBBytes) + (size_t)a * kABytes * mb + sizeof(MmaSmemTail) <= 227 * 1024) {
       g.na = a;
       g.nb = b;
     }
   }
-  // CTA pair (cta_group::2): the two CTAs of a cluster work on the same database tile and different super-blocks;
-  // one M=256 MMA spans both SMs, each CTA stages only its 128 of the tile's 256 rows (no multicast needed)
-  const int two = (g.share == kShareX && env_int("RIR_MMA_TWO", 1) != 0) ? 1 : 0;
-  if (two) {
+  if (two)
     g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-    g.na = g.nb = mb == 1 ? 6 : 4;
-  }
   const int ca = (!two && g.share == kShareQ) ? g.csize : 1, cb = two ? 2 : (g.share == kShareX ? g.csize : 1);
   // one small query block: load only the rows that exist (multiple of 8 rows per sharer: 1024-byte swizzle atoms)
   g.a_rows = kTileM;
@@ -847,13 +926,14 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     g.a_rows = (p.nq + unit - 1) / unit * unit;
     if (g.a_rows > kTileM) g.a_rows = kTileM;
   }
-  g.nqg = g.share == kShareX ? (g.nsb + g.csize - 1) / g.csize : g.nsb;
+  // super-blocks per cluster item: a pair (or a 2-cluster) takes two neighbouring super-blocks
+  g.nqg = g.share == kShareX ? (g.nsb + 1) / 2 : g.nsb;
   long long cluster_items;
   if (g.share == kShareQ) cluster_items = (g.ntiles + g.csize - 1) / g.csize;
-  else if (g.share == kShareX) cluster_items = g.ntiles * g.nqg;
+  else if (g.share == kShareX) cluster_items = ((g.ntiles + g.npairs - 1) / g.npairs) * g.nqg;
   else cluster_items = g.ntiles * g.nsb;
   if (cluster_items <= 0) return RIR_OK;
-  long long nclusters = sms / g.csize;
+  long long nclusters = h.max_ctas / g.csize;
   if (nclusters > cluster_items) nclusters = cluster_items;
   g.rounds = (cluster_items + nclusters - 1) / nclusters;
   const unsigned grid = (unsigned)(nclusters * g.csize);
@@ -863,11 +943,13 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
   g.ra_rounds = 0;
   if (g.fused) {
     // first phase: every (query, tile v < grid) pair — one tile per CTA and query
-    if ((int)grid != sms || g.ntiles < 2ll * grid) {
+    if ((int)grid != h.max_ctas || g.ntiles < 2ll * grid) {
       set_error("sim_topk(mma): fused scan needs a full grid (internal error: mma_can_fuse not honoured)");
       return RIR_E_ARG;
     }
-    g.ra_rounds = g.share == kShareQ ? 1 : (g.share == kShareX ? g.nqg * g.csize : g.nsb);
+    // rounds until every query has met `grid` tiles: a cluster item covers csize tiles (shared query chunk), or
+    // npairs tiles x 2 super-blocks (shared database chunk / CTA pairs: 2 * nqg rounds either way)
+    g.ra_rounds = g.share == kShareQ ? 1 : (g.share == kShareX ? g.nqg * 2 : g.nsb);
     p.topt = kFusedTopT;
     p.fused_tiles = (int)grid;
     p.sample_m = (int)grid * kFusedTopT;
@@ -880,7 +962,7 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     p.perm_mul = mul;
   }
   CUtensorMap tmQ, tmX;
-  if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, g.a_rows / ca)) return e;
+  if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, two ? g.a_rows / g.npairs : g.a_rows / ca)) return e;
   if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, g.tile_n / cb)) return e;
   if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, grid, mb, two, st);
   return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, grid, mb, two, st);
