@@ -47,7 +47,8 @@ constexpr int kABytes = kTileM * 128;  // 16 KB: 128 queries x 128 B of K
 constexpr int kBBytes = kTileN * 128;  // 32 KB: 256 database rows x 128 B of K
 constexpr int kMaxSlots = 8;
 constexpr int kTmemCols = 512;
-constexpr int kPend = 8;     // per-thread staged candidates before one atomicAdd reserves their slots
+constexpr int kPend = 16;    // per-thread staged candidates before one atomicAdd reserves their slots (>= 16: a
+                             // 16-column unit's survivors always fit after a reservation)
 constexpr int kMaxTopT = 8;  // keys kept per (query, sample tile)
 static_assert(kFusedTopT <= kMaxTopT, "fused sample keeps at most kMaxTopT keys");
 
@@ -567,6 +568,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             mask |= __hge2_mask(__floats2bfloat162_rn(sc[2 * j], sc[2 * j + 1]), ts2) & (0x00010001u << j);
           // qvalid: lanes of queries that do not exist hold whatever the (trimmed) query box left in shared memory
           if (!qvalid) mask = 0u;
+          // room for all of this unit's survivors is made BEFORE the loop, so the loop body stays tiny
+          if (mask != 0u && npend + __popc(mask) > kPend) reserve();
 #pragma unroll 1
           while (mask) {  // rare: ~k*n/S survivors per query over the whole scan
             const int b = __ffs(mask) - 1;
@@ -574,10 +577,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             const int j = ((b & 15) << 1) | (b >> 4);
             const float s1 = pick16(sc, j);
             const long long row = row0 + c0 + j;
-            if (row < p.n && passes(s1, (uint32_t)row, ts, ti)) {
-              if (npend == kPend) reserve();
-              pend[cur][npend++] = make_key(s1, (uint32_t)row);
-            }
+            if (row < p.n && passes(s1, (uint32_t)row, ts, ti)) pend[cur][npend++] = make_key(s1, (uint32_t)row);
           }
         } else if (qvalid) {
           if (mode == kModeSample && p.topt > 0) {
@@ -830,9 +830,10 @@ static MmaShape plan_shape(int nq) {
   const int sms = sm_count();
   MmaShape h;
   h.nqb = (nq + kTileM - 1) / kTileM;
-  // Measured on B200 (1M x 2048 bf16): CTA pair + one block per CTA (epilogue overlapped with the next tile's MMAs)
-  // 1220 TFLOP/s at 1024 queries; pair + two blocks per CTA 1110 (its epilogue is not overlapped); no pair 1074-1107.
-  h.mb = 1;
+  // Measured on B200 (1M x 2048 bf16), CTA pairs: one block per CTA (epilogue overlapped with the next tile's MMAs)
+  // 1185 TFLOP/s at 1024 queries and 1162 at 4096; two blocks per CTA (a third fewer bytes ingested per flop, but its
+  // epilogue is not overlapped) 1174 and 1245 — and 1415 with the epilogue switched off.  Without pairs 1074-1107.
+  h.mb = h.nqb >= 16 ? 2 : 1;
   {
     const int o = env_int("RIR_MMA_MB", 0);  // tuning override (development only)
     if (o == 1 || o == 2) h.mb = o;
