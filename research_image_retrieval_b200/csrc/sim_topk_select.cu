@@ -273,14 +273,21 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
   }
   __syncthreads();
   for (int s = threadIdx.x; s < slots; s += blockDim.x) {
-    const unsigned long long last = keys[(size_t)s * T + T - 1];
+    unsigned long long kk[kFusedTopT];  // the slot's keys in one round of independent loads (T == kFusedTopT)
+#pragma unroll
+    for (int i = 0; i < kFusedTopT; ++i) kk[i] = i < T ? keys[(size_t)s * T + i] : 0ull;
+    unsigned long long last = kk[0];
+#pragma unroll
+    for (int i = 1; i < kFusedTopT; ++i)
+      if (i < T) last = kk[i];
     if (last != 0ull && key_score(last) >= ts) {
       const int i = atomicAdd(s_nredo, 1);
       if (i < kMaxRedo) s_redo[i] = s;
     } else {
-      for (int i = 0; i < T; ++i) {
-        const unsigned long long key = keys[(size_t)s * T + i];
-        if (key != 0ull && key_score(key) >= ts) {
+#pragma unroll
+      for (int i = 0; i < kFusedTopT; ++i) {
+        const unsigned long long key = kk[i];
+        if (i < T && key != 0ull && key_score(key) >= ts) {
           const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
           if (pos < (uint32_t)p.cap) c[pos] = key;
         }
