@@ -134,6 +134,13 @@ int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, 
  * call's stream.  Pass NULL, NULL to disarm.  The events must outlive the calls; timing is read by the caller. */
 int rir_profile_scan_events(void* ev_start, void* ev_stop);
 
+/* Development hook: event timeline of the tcgen05 scan.  dev_buf = device buffer of (1 + 2 * cap_events) uint64, zeroed
+ * by the caller; the following rir_sim_topk calls of THIS host thread append (meta, %globaltimer ns) pairs —
+ * meta = cta << 32 | event << 16 | round; events: 0 kernel start, 1 first database TMA of the round, 2 MMA round start,
+ * 3 MMA round issued, 4 accumulator ready (epilogue), 5 epilogue of the round done, 6 threshold phase begin, 7 grid
+ * barrier passed, 8 all thresholds published, 9 CTA done.  NULL disarms.  See tools/timeline.py. */
+int rir_profile_timeline(void* dev_buf, int cap_events);
+
 /* Re-score a candidate list with higher-precision rows and keep the best k (same order rule).  Used after an fp8
  * scan that returned k_in > k candidates, so the final list meets the fp8 bar "5e-3 relative against an fp32 rescore".
  *   Q[nq,d], X[n_local,d] in dtype RIR_BF16 or RIR_F32 (the rescoring copy of the shard); ix_in[nq,k_in] GLOBAL row

@@ -38,6 +38,7 @@ SIGNATURES = {
     "rir_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
                              c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "rir_profile_scan_events": (c_int, [c_void_p, c_void_p]),
+    "rir_profile_timeline": (c_int, [c_void_p, c_int]),
     "rir_rescore_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rir_merge_topk_workspace": (c_size_t, [c_int, c_int, c_int]),

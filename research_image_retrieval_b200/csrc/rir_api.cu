@@ -124,6 +124,16 @@ extern "C" int rir_profile_scan_events(void* ev_start, void* ev_stop) {
   return RIR_OK;
 }
 
+// optional development hook: event timeline of the tcgen05 scan kernels launched by this host thread
+static thread_local unsigned long long* g_timeline = nullptr;
+static thread_local int g_timeline_cap = 0;
+
+extern "C" int rir_profile_timeline(void* dev_buf, int cap_events) {
+  g_timeline = reinterpret_cast<unsigned long long*>(dev_buf);
+  g_timeline_cap = dev_buf ? cap_events : 0;
+  return RIR_OK;
+}
+
 extern "C" int rir_version(void) { return RIR_VERSION; }
 extern "C" const char* rir_last_error(void) { return g_err; }
 extern "C" int rir_device_check(void) { return check_arch(); }
@@ -238,6 +248,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
 
     p.nq = gq;
     p.k = k;
+    p.timeline = g_timeline;
+    p.timeline_cap = g_timeline_cap;
     if (ex) {
       p.ex = *ex;
       p.ex.q_base = g0;
@@ -252,7 +264,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
       p.mode = kModeScanAll;
     } else if (!use_stream && mma_can_fuse(gq, n_local, k)) {
       // ONE launch: the first round of the scan is the sample, tau is derived inside the kernel (sim_topk_mma.cu)
-      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (2 * align_up((size_t)pl.group, 128) + 16) * sizeof(uint32_t), st));
+      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (align_up((size_t)pl.group, 128) + 16) * sizeof(uint32_t), st));
+      RIR_CUDA_OK(cudaMemsetAsync(p.tau_score, 0xFF, (size_t)gq * sizeof(float), st));  // kTauUnset
       if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
       if (int e = run_pass(kModeFused)) return e;
       if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));

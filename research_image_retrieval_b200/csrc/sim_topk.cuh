@@ -21,6 +21,7 @@ namespace rir {
 constexpr int kSampleBlockRows = 256;  // rows per sample block == MMA tile N
 
 enum SimMode : int { kModeScanFilter = 0, kModeSample = 1, kModeScanAll = 2, kModeFused = 3 };
+constexpr uint32_t kTauUnset = 0xFFFFFFFFu;  // tau_score[q] before the fused scan has published it (a NaN pattern)
 constexpr int kFusedTopT = 8;  // keys kept per (query, first-phase tile) in the fused scan
 
 // Sharded search without a collective library call: every rank owns an INBOX in its HBM that all peers can write
@@ -83,13 +84,16 @@ struct SimParams {
   // scan kernel and the remaining rounds filter with it.  Tiles are visited in a multiplicative permutation so the
   // first `fused_tiles` of them are spread over the whole shard.
   uint32_t* gbar;        // [2] grid-barrier counters (zeroed by the host before the launch)
-  uint32_t* tau_flag;    // [nq_total] set (release) once tau_score[q] is published (zeroed by the host)
+  uint32_t* tau_flag;    // (unused: tau_score[q] carries its own "published" sentinel, kTauUnset)
   int fused_tiles;       // first-phase tiles == slots per query in sample_keys / kFusedTopT
   long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
   long long perm_n;      // number of database tiles
   int tile_rows;         // rows per database tile of the fused scan (256 or 128)
   int k;                 // top-k requested (the fused scan computes tau itself)
   Exchange ex;           // sharded search: push the local top-k to the peers instead of writing out_score / out_idx
+  // development: per-CTA event timeline of the tcgen05 scan (rir_profile_timeline); null in production
+  unsigned long long* timeline;  // [0] = event counter, then (meta, globaltimer ns) pairs
+  int timeline_cap;              // events that fit
 };
 
 // first row of sample block j (strided over the whole shard so clustered / sorted databases are sampled fairly)

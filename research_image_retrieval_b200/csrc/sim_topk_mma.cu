@@ -117,16 +117,31 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// development timeline (rir_profile_timeline): one (meta, time) pair per call; no-op when not armed
+__device__ __forceinline__ void tl_mark(const SimParams& p, int event, long long round) {
+  if (p.timeline == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned long long i = atomicAdd(p.timeline, 1ull);
+  if (i < (unsigned long long)p.timeline_cap) {
+    p.timeline[1 + 2 * i] = ((unsigned long long)blockIdx.x << 32) | ((unsigned long long)event << 16) |
+                            (unsigned long long)(round & 0xffff);
+    p.timeline[2 + 2 * i] = t;
+  }
+}
+
 // one thread per CTA: arrive on a global counter and wait until all `expected` CTAs have (bounded: a bug must trap)
 __device__ __forceinline__ void grid_arrive_wait(uint32_t* ctr, uint32_t expected) {
-  __threadfence();
-  atomicAdd(ctr, 1u);
+  // Arrive with a release reduction (no return value to wait for), poll with relaxed loads (an acquire load per poll
+  // would invalidate L1 every time), fence once at the end.  Under a bandwidth-saturating scan every L2 round trip
+  // costs microseconds (tools/timeline.py), so the barrier is kept to the minimum number of them.
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
   const long long t0 = clock64();
   while (true) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= expected) break;
-    __nanosleep(40);
+    __nanosleep(20);
     if (clock64() - t0 > 8000000000ll) {
       printf("librir: grid barrier timed out (block %d: %u of %u arrived)\n", (int)blockIdx.x, v, expected);
       __trap();
@@ -139,7 +154,7 @@ constexpr int kMaxFusedKeys = 1280;  // first-phase keys per query the in-kernel
 
 // All epilogue threads (NE = 128 or 256): tau for query q = lower edge of the 24-bit bucket that holds the k-th best
 // kept key.  The keys are read once into registers; three 8-bit radix passes run on a shared-memory histogram.
-// Publishes tau_score[q] and then tau_flag[q] (release) — readers spin on the flag, there is no second grid barrier.
+// Publishes tau_score[q] over its sentinel (release) — readers poll the value, there is no second grid barrier.
 template <int NE>
 __device__ __forceinline__ void cta_fused_tau(const SimParams& p, int q, int k, MmaSmemTail* tail, int etid) {
   constexpr int KPT = kMaxFusedKeys / NE;
@@ -206,11 +221,12 @@ __device__ __forceinline__ void cta_fused_tau(const SimParams& p, int q, int k, 
     bar();
   }
   if (etid == 0) {
+    // tau_score[q] itself is the flag: the host pre-set it to the sentinel kTauUnset (a NaN pattern no threshold can
+    // be); readers poll the value — one L2 round trip less than a separate flag, and under a bandwidth-saturating scan
+    // every dependent L2 access costs microseconds.
     const float tau = tail->tau_nz >= (uint32_t)k ? ordered_to_float(prefix << 8) : -INFINITY;
-    p.tau_score[q] = tau;
     p.tau_idx[q] = 0xFFFFFFFFu;  // every index passes at score == tau
-    __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.tau_flag + q), "r"(1u) : "memory");
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.tau_score + q), "r"(__float_as_uint(tau)) : "memory");
   }
 }
 
@@ -296,6 +312,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   if (g.csize > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  if (threadIdx.x == 0) tl_mark(p, 0, 0);
 
   // virtual tile -> first database row.  Dummy tiles (v >= ntiles) start past the last row (all-OOB loads).
   auto tile_row0 = [&](long long v) -> long long {
@@ -322,6 +339,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         const int row0 = (int)tile_row0(v);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_b[s], ph ^ 1u);
+          if (kc == 0) tl_mark(p, 1, rd);
           uint8_t* dst = ring_b + (size_t)s * kBSlot;
           if (TWO) {  // my 128 rows into my shared memory; both halves complete on the leader's barrier
             if (leader) mbar_expect_tx(&tail->full_b[s], b_bytes);
@@ -390,6 +408,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       for (long long rd = 0; rd < g.rounds; ++rd) {
         mbar_wait(&tail->tmem_empty[ab], aph ^ 1u);
         tc_fence_after();
+        tl_mark(p, 2, rd);
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kBufCols);
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->full_a[sa], pha);
@@ -427,6 +446,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         }
         // accumulators complete -> epilogue (of both CTAs of a pair)
         if (TWO) umma_commit_2sm(&tail->tmem_full[ab], pair_mask); else umma_commit(&tail->tmem_full[ab]);
+        tl_mark(p, 3, rd);
         if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
       }
     }
@@ -472,28 +492,21 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     };
     // fused: publish the first-phase keys, then compute (and publish) tau for this CTA's share of the queries
     auto fused_threshold = [&]() {
-      __threadfence();
+      if (etid == 0) tl_mark(p, 6, 0);
+      // bar.sync orders every epilogue thread's key stores before thread 0's release-arrive (cumulativity: the same
+      // pattern as cooperative groups' grid sync) — no per-thread fence, one L2 round trip less
       epi_bar();
       if (etid == 0) grid_arrive_wait(&p.gbar[0], gridDim.x);
       epi_bar();
-      for (int q = (int)blockIdx.x; q < p.nq; q += (int)gridDim.x) cta_fused_tau<kEpiThreads>(p, q, p.k, tail, etid);
-      // every tau this CTA will read is published by some CTA's loop above: wait for all flags once (no acquire /
-      // L1 invalidate per round later), then one fence
-      for (int q = etid; q < p.nq; q += kEpiThreads) {
-        const long long t0 = clock64();
-        while (true) {
-          uint32_t f;
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.tau_flag + q) : "memory");
-          if (f != 0u) break;
-          __nanosleep(40);
-          if (clock64() - t0 > 8000000000ll) {
-            printf("librir: fused threshold of query %d never arrived (block %d)\n", q, (int)blockIdx.x);
-            __trap();
-          }
-        }
+      if (etid == 0) tl_mark(p, 7, 0);
+      if (p.nq >= (int)gridDim.x) {
+        for (int q = (int)blockIdx.x; q < p.nq; q += (int)gridDim.x) cta_fused_tau<kEpiThreads>(p, q, p.k, tail, etid);
+      } else {
+        // fewer queries than CTAs: every CTA computes one (several CTAs the same query — they publish the same value,
+        // and the readers get the fastest replica: the tail of the L2 latency under load is what they wait for)
+        cta_fused_tau<kEpiThreads>(p, (int)blockIdx.x % p.nq, p.k, tail, etid);
       }
-      __threadfence();
-      epi_bar();
+      if (etid == 0) tl_mark(p, 8, 0);
     };
     bool tau_ready = !g.fused;
     const bool scaled = p.q_scale != nullptr || p.x_scale != nullptr;  // bf16 rows: scores are the raw accumulators
@@ -522,7 +535,21 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       uint32_t ti = 0;
       float qsc = 1.f;
       if (qvalid) {
-        if (mode == kModeScanFilter) {
+        if (mode == kModeScanFilter && g.fused) {  // published by whichever CTA computed it: poll the value itself
+          uint32_t bits;
+          const long long t0 = clock64();
+          while (true) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bits) : "l"(p.tau_score + q) : "memory");
+            if (bits != kTauUnset) break;
+            __nanosleep(20);
+            if (clock64() - t0 > 8000000000ll) {
+              printf("librir: fused threshold of query %d never arrived (block %d)\n", q, (int)blockIdx.x);
+              __trap();
+            }
+          }
+          ts = __uint_as_float(bits);
+          ti = 0xFFFFFFFFu;
+        } else if (mode == kModeScanFilter) {
           ts = __ldcg(&p.tau_score[q]);
           ti = __ldcg(&p.tau_idx[q]);
         }
@@ -540,14 +567,14 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       }
       mbar_wait(&tail->tmem_full[ab], aph);
       tc_fence_after();
+      if (etid == 0) tl_mark(p, 4, rd);
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * kBufCols + mblk * kTileN);
       // 16 columns at a time, double buffered: the tcgen05.ld of the next unit is in flight while this one is
       // processed (TMEM loads take a few hundred clocks while the MMAs of the other accumulator are running).
       // Survivors are found with a per-lane bitmask — no divergent per-column branches (the unrolled 32-way version
       // of this code took ~27k clocks per tile, 10x the budget) — and each lane then walks ITS bits, fetching the
       // score from registers with a select tree, so the score array is never indexed dynamically.
-      auto process16 = [&](const uint32_t (&vv)[16], int c0) {
-        float sc[16];
+      auto scores16 = [&](const uint32_t (&vv)[16], int c0, float (&sc)[16]) {
         if (p.x_scale) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]) * qsc * tail->xs[xb][c0 + j];
@@ -558,6 +585,36 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) sc[j] = __uint_as_float(vv[j]);
         }
+      };
+      // First-phase pre-pass: the 8th largest of the tile's 16 unit maxima is a lower bound of the lane's final 8th
+      // best score (8 distinct columns reach it), so the collecting pass can start with that threshold instead of
+      // -inf: ~12 insertions per lane instead of ~50 (and far less divergence: every lane inserts exactly once per
+      // unit here).  Costs a second read of the tile from TMEM.
+      float t8[kMaxTopT];
+#pragma unroll
+      for (int i = 0; i < kMaxTopT; ++i) t8[i] = -INFINITY;
+      auto prepass16 = [&](const uint32_t (&vv)[16], int c0) {
+        float sc[16];
+        scores16(vv, c0, sc);
+        if (row0 + c0 + 16 > p.n) {  // last, partial tile: columns past the shard do not count
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (row0 + c0 + j >= p.n) sc[j] = -INFINITY;
+        }
+        float m = sc[0];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) m = fmaxf(m, sc[j]);
+#pragma unroll
+        for (int i = 0; i < kMaxTopT; ++i) {  // branch-free insertion of m into the descending list t8
+          const float hi = fmaxf(t8[i], m);
+          m = fminf(t8[i], m);
+          t8[i] = hi;
+        }
+      };
+      float thr0 = -INFINITY;  // set by the pre-pass (first-phase rounds only)
+      auto process16 = [&](const uint32_t (&vv)[16], int c0) {
+        float sc[16];
+        scores16(vv, c0, sc);
         if (mode == kModeScanFilter) {
           // pre-filter on packed bf16 pairs (3 instructions per 2 columns): round-to-nearest is monotonic, so
           // score >= ts implies bf16(score) >= bf16(ts) — it can only let extra columns through, which the exact fp32
@@ -586,7 +643,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
 #pragma unroll
             for (int i = 1; i < kMaxTopT; ++i)
               if (i < p.topt) last = top[i];
-            const float thr = last != 0ull ? key_score(last) : -INFINITY;
+            const float thr = last != 0ull ? fmaxf(key_score(last), thr0) : thr0;
             uint32_t mask = 0u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) mask |= (sc[j] >= thr) ? (1u << j) : 0u;
@@ -597,6 +654,8 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
               const long long row = row0 + c0 + j;
               unsigned long long key = make_key(pick16(sc, j), (uint32_t)row);
               if (row < p.n && key > last) {
+                // (a rank-based insertion — position by independent compares, every slot rewritten — was tried to
+                //  shorten the dependency chain: slower, 30 vs 24.5 us for the first-phase tile.)
 #pragma unroll
                 for (int i = 0; i < kMaxTopT; ++i) {  // insertion into the sorted (descending) top list
                   if (i < p.topt && key > top[i]) {
@@ -632,6 +691,19 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       };
       if (!(g.debug & 2)) {
         uint32_t va[16], vb[16];
+        if (mode == kModeSample && p.topt == kMaxTopT && g.tile_n >= 16 * kMaxTopT) {  // (uniform) first-phase pre-pass
+          tmem_ld_32x32_x16(taddr, va);
+#pragma unroll 1
+          for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
+            tmem_ld_wait();
+            tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 16), vb);
+            prepass16(va, c0);
+            tmem_ld_wait();
+            if (c0 + 32 < g.tile_n) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
+            prepass16(vb, c0 + 16);
+          }
+          thr0 = t8[kMaxTopT - 1];
+        }
         tmem_ld_32x32_x16(taddr, va);
 #pragma unroll 1
         for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
@@ -645,6 +717,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       }
       tc_fence_before();
       __syncwarp();
+      if (etid == 0) tl_mark(p, 5, rd);
       if (lane == 0) {
         if (TWO) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[ab]), leader_rank));  // my pair's MMA thread
         else mbar_arrive(&tail->tmem_empty[ab]);
@@ -662,6 +735,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tl_mark(p, 9, 0);
   if (g.csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / signal it
   if (warp == 2) {
     tc_fence_after();
