@@ -691,7 +691,9 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       };
       if (!(g.debug & 2)) {
         uint32_t va[16], vb[16];
-        if (mode == kModeSample && p.topt == kMaxTopT && g.tile_n >= 16 * kMaxTopT) {  // (uniform) first-phase pre-pass
+        // (uniform) first-phase pre-pass — pays off once many lanes collect at the same time (divergence); with a
+        // handful of queries the second TMEM pass costs more than it saves (1 query, 126 k-row shard: +4 us)
+        if (mode == kModeSample && p.topt == kMaxTopT && g.tile_n >= 16 * kMaxTopT && p.nq >= 16) {
           tmem_ld_32x32_x16(taddr, va);
 #pragma unroll 1
           for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
