@@ -501,9 +501,10 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       if (etid == 0) tl_mark(p, 7, 0);
       if (p.nq >= (int)gridDim.x) {
         for (int q = (int)blockIdx.x; q < p.nq; q += (int)gridDim.x) cta_fused_tau<kEpiThreads>(p, q, p.k, tail, etid);
-      } else {
-        // fewer queries than CTAs: every CTA computes one (several CTAs the same query — they publish the same value,
-        // and the readers get the fastest replica: the tail of the L2 latency under load is what they wait for)
+      } else if ((int)blockIdx.x < 4 * p.nq) {
+        // fewer queries than CTAs: up to four CTAs compute the same query — they publish the same value and the readers
+        // get the fastest replica (the tail of the L2 latency under load is what they wait for).  Not more: 148 CTAs
+        // reading one query's keys at once is an L2 hot spot (1 query, 126 k-row shard: +4 us).
         cta_fused_tau<kEpiThreads>(p, (int)blockIdx.x % p.nq, p.k, tail, etid);
       }
       if (etid == 0) tl_mark(p, 8, 0);
