@@ -5,14 +5,15 @@
 // without ever writing the [nq, n] score matrix to HBM.
 //
 // Scheme (exact):
-//   1. SAMPLE pass  : score `sblk` strided 256-row blocks of the shard; keep, per query, the best few keys of every
-//                     CTA / warp (sample_keys) — or all sampled scores (sample_scores) when k is large.
-//   2. threshold    : tau[q] = k-th best (score, index) key among the kept ones.  They are scores of distinct rows
-//                     of the shard, so tau[q] <= the true k-th best key: filtering with it can never drop a top-k row.
-//   3. SCAN pass    : score every row once; rows whose key >= tau[q] are appended to cand[q, cap] (rare: ~k*n/S).
-//   4. final select : exact top-k of cand[q] (radix select + bitonic sort) -> out.
-//   5. fallback     : a query whose candidate list overflowed `cap` (adversarial row order) is re-done by the
-//                     one-CTA-per-query exact kernel.  Small shards (n <= cap) skip 1-2 and push every row.
+//   1. SAMPLE       : score a spread-out subset of 256-row blocks; keep, per query, the best few keys of every block.
+//   2. threshold    : tau[q] = (a lower bound of) the k-th best key among the kept ones.  They are scores of distinct
+//                     rows of the shard, so tau[q] <= the true k-th best key: filtering can never drop a top-k row.
+//   3. SCAN         : score every row once; rows whose key >= tau[q] are appended to cand[q, cap] (rare: ~k*n/S).
+//   4. final select : exact top-k of cand[q] (radix select + bitonic sort) -> out (or -> the peers' inboxes).
+//   5. overflow     : a query whose candidate list overflowed `cap` (adversarial row order) is redone by a
+//                     one-CTA exact scan.  Small shards (n <= 16384) skip 1-2 and keep every row.
+// tcgen05 path (kModeFused): 1-3 are ONE launch — the first round of the scan is the sample, tau is derived inside
+// the kernel behind a grid barrier (sim_topk_mma.cu).  Stream path / large k: three launches (sample, threshold, scan).
 #pragma once
 #include "rir_common.cuh"
 

@@ -9,31 +9,37 @@
 //   warp 3      TMA producer, query ring    : MB x (<=128 queries x 128 B of K) (L2 resident)
 //   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=256, K=16|32) — fp32 accumulators in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..   epilogue (4 warps per query block): tcgen05.ld 32 lanes x 32 columns; thread == one query; running
-//               max against the query's threshold tau; rare survivors are staged per thread and appended to the
-//               candidate list with one atomicAdd per flush
+//   warps 4..   epilogue (4 warps per query block): tcgen05.ld 32 lanes x 16 columns, double buffered; thread == one
+//               query; packed-bf16 pre-filter against the query's threshold tau -> per-lane bitmask; the rare
+//               survivors are picked out of registers with a select tree, checked exactly in fp32, staged per thread
+//               and appended to the candidate list with one deferred atomicAdd per batch
 // Work item = (database tile, query super-block of MB x 128 queries).
-//   MB = 1 : two 256-column accumulators, the epilogue of one tile overlaps the MMAs of the next (HBM-bound batches)
-//   MB = 2 : two query blocks share every database chunk in shared memory (512 TMEM columns, one buffer).
-//            Measured on B200 this kernel is bound by the bytes DELIVERED INTO the SM (l1tex__m_xbar2l1tex_read_bytes
-//            ~8.6 TB/s chip-wide = ~32 B/clk/SM, multicast copies included), not by L2 or HBM: a 128x256 tile needs
-//            48 KB per 512 MMA clocks, a 256x256 tile 64 KB per 1024 — hence MB = 2 for tensor-bound batches, and
-//            the query box is trimmed to the real number of queries for single-block batches.
+//   MB = 1 : two 256-column accumulators, the epilogue of one tile overlaps the MMAs of the next
+//   MB = 2 : two query blocks share every database chunk in shared memory (512 TMEM columns, one buffer: the epilogue
+//            is not overlapped) — used from 2048 queries.
+// What bounds the tensor regime (measured on B200): the bytes each SM ingests per flop — a 128x256 tile
+// needs 48 KB per 512 MMA clocks (33% of the tensor pipe), a CTA pair 32 KB (52%), a pair with MB = 2 48 KB per 1024.
+// For single-block batches the query box is trimmed to the real number of queries.
 //
-// Thread-block clusters of 2 cut the L2 reads:
+// Thread-block clusters of 2:
 //   one super-block   : the CTAs of a cluster take DIFFERENT database tiles and SHARE the query chunk — each CTA
-//                       loads 1/C of its rows and TMA-multicasts them to all C shared memories;
-//   several           : the CTAs of a cluster take the SAME database tile and different super-blocks — the
-//                       database chunk is the multicast operand.
-// A multicast slot may only be refilled once every CTA of the cluster has consumed it: the MMA warp's
-// tcgen05.commit for that ring is multicast to the `empty` barrier of all C CTAs (barrier count C).
+//                       loads half of its rows and TMA-multicasts them to both shared memories;
+//   several           : CTA PAIR (TWO, cta_group::2) — the two CTAs take the SAME database tile and neighbouring
+//                       super-blocks; ONE M=256 tcgen05.mma issued by the leader spans both SMs, each CTA stages only
+//                       its 128 of the tile's 256 rows and its own queries; every TMA load completes on the leader's
+//                       barriers, tcgen05.commit (multicast) frees ring slots and publishes accumulators in both CTAs.
+//                       (Without TWO — RIR_MMA_TWO=0 — the database chunk is multicast instead.  RIR_MMA_CLUSTER4=1:
+//                       two pairs per cluster that multicast the query chunk to each other; measured slower.)
+// A multicast slot may only be refilled once every CTA that shares it has consumed it: the MMA thread's
+// tcgen05.commit for that ring is multicast to the `empty` barrier of all sharers.
 //
 // Fused mode (kModeFused): no separate sample / threshold launches.  The first `ra_rounds` rounds of the scan are
-// the sample: the epilogue keeps the best kFusedTopT keys per (query, tile) in sample_keys; a grid barrier follows
-// (all CTAs are co-resident: one per SM); every epilogue warp then derives tau for a few queries (3-pass radix over
+// the sample: the epilogue keeps the best kFusedTopT keys per (query, tile) in sample_keys (a pre-pass over the
+// tile's unit maxima gives the collecting pass its starting threshold); ONE grid barrier follows (all CTAs are
+// co-resident: one per SM); the epilogue threads of every CTA then derive tau for a few queries (3-pass radix over
 // the top 24 key bits: tau = lower edge of the bucket holding the k-th best kept key — still a lower bound of the
-// true k-th best, so the filter stays exact); a second grid barrier publishes tau and the remaining rounds filter.
-// The TMA / MMA warps keep running through the barriers (prefetching the next tile), so the bubble is hidden.
+// true k-th best, so the filter stays exact) and publish it in place over a sentinel; the remaining rounds poll
+// their query's tau and filter.  The TMA / MMA warps keep running through the barrier (prefetching the next tiles).
 // The first-phase keys are merged into the candidate list by final_select_kernel (sim_topk_select.cu).
 #include <cuda.h>
 #include <stdlib.h>
