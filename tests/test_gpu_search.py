@@ -495,7 +495,8 @@ BOUNDARY_CASES = [
     (1, 76000, 2048, 1, "bf16"),      # k = 1, one query, full-width rows
     (3, 76000, 64, 592, "bf16"),      # largest k of the fused route (148 * 8 >= 2k)
     (3, 76000, 64, 593, "bf16"),      # first k of the three-launch route
-    (2, 40000, 64, 4096, "bf16"),     # large k: dense sample, separate exact fallback kernel route
+    (2, 40000, 64, 4096, "bf16"),     # large k: dense sample; overflow redo still inside the select kernel
+    (2, 40000, 64, 8192, "bf16"),     # largest k: the separate exact-scan fallback launch
     (70, 80000, 4096, 20, "bf16"),    # 8 KB rows: 64 K-chunks per tile
     (16, 77000, 16, 5, "fp8"),        # a single 16-byte chunk per row
 ]
