@@ -12,7 +12,7 @@ from .helpfunc import extract_database, extract_vectors, extract_vectors_device,
 from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, gem, gem_pool, l2n, mac_pool, spoc,  # noqa: F401
                       spoc_pool, ultron_gem_pooling, whiten)
 from .search import (Database, ShardedDatabase, alpha_query_expansion, merge_topk, pack_descriptors, rank,  # noqa: F401
-                     search_with_aqe, shard_bounds, sim_topk)
+                     rerank_topk, search_with_aqe, shard_bounds, sim_topk)
 
 from .formats import DescriptorStore, RoxfordAndRparis, gnd_to_csr  # noqa: F401
 from .whitening import ConvDimReduction, pca_covariance, pcawhitenlearn_shrinkage  # noqa: F401

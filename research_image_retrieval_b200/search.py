@@ -499,3 +499,31 @@ def search_with_aqe(db, q_rows, q_scale, k: int = 100, kq: int = 10, alpha: floa
     q2, q2s, q2f = alpha_query_expansion(db, q_rows, q_scale, sc, ix, kq=kq, alpha=alpha)
     sc2, ix2 = db.search(q2, q2s, k, path=path)
     return sc2, ix2, q2f
+
+
+# ----------------------------------------------------------------------------------------------
+# re-ranking hook
+# ----------------------------------------------------------------------------------------------
+def rerank_topk(scores: torch.Tensor, idx: torch.Tensor, pair_score_fn, top_r: Optional[int] = None):
+    """Hook for a pairwise re-ranker over the top of each list (CVNet-Rerank / SuperGlobal style: the reference only has
+    the stub `CVNet_Rerank.forward(query_img, key_img) -> score`, models/cvnet_modules/CVNet_Rerank_model.py:49-74, and
+    lists both methods on its roadmap, memo.md:46-55).
+
+    scores / idx: [nq, k] from a search (GPU).  `pair_score_fn(q_ids [nq], cand_idx [nq, r]) -> new scores [nq, r]`
+    (fp32 CUDA tensor; -1 candidates may get any score) is the caller's model.  The first r = top_r (default k)
+    candidates of every query are re-sorted by the new score (descending, ties -> ascending index, by
+    rir_merge_topk); the tail keeps its order behind them.  Returns (scores, idx) [nq, k]: the head carries the new
+    scores, the tail the old ones."""
+    nq, k = idx.shape
+    r = k if top_r is None else max(0, min(int(top_r), k))
+    if r == 0 or nq == 0:
+        return scores, idx
+    head_i = idx[:, :r].contiguous()
+    q_ids = torch.arange(nq, device=idx.device)
+    new = pair_score_fn(q_ids, head_i)
+    if not (isinstance(new, torch.Tensor) and new.is_cuda and tuple(new.shape) == (nq, r)):
+        raise ValueError(f"pair_score_fn must return a CUDA tensor of shape {(nq, r)}")
+    hs, hi = merge_topk(new.float().contiguous()[None], head_i[None])
+    if r == k:
+        return hs, hi
+    return torch.cat([hs, scores[:, r:]], 1), torch.cat([hi, idx[:, r:]], 1)

@@ -512,3 +512,28 @@ def test_tensor_path_boundaries(cuda_device, nq, n, d, k, dtype):
     Xf = _dequant(db.rows, db.scale, dtype)[:, :d]
     Qf = _dequant(qr, qs, dtype)[:, :d]
     _check(sc, ix, Qf, Xf, k, 1e-3)
+
+
+def test_rerank_hook(cuda_device):
+    """a pairwise re-ranker re-orders the head of every list; the tail stays put."""
+    nq, n, d, k = 5, 30000, 64, 40
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=5)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, qs = db.pack_queries(Q.to(cuda_device))
+    sc, ix = db.search(qr, qs, k)
+    Xf = X.to(cuda_device)
+
+    def fp32_pair_scores(q_ids, cand):                     # a stand-in "model": exact fp32 cosine of the pair
+        return torch.einsum("qrd,qd->qr", Xf[cand.long()], Q.to(cuda_device)[q_ids])
+
+    rs, ri = rir.rerank_topk(sc, ix, fp32_pair_scores, top_r=25)
+    assert torch.equal(ri[:, 25:], ix[:, 25:]) and torch.equal(rs[:, 25:], sc[:, 25:])
+    assert torch.equal(torch.sort(ri[:, :25], 1).values, torch.sort(ix[:, :25], 1).values)   # same candidates
+    assert bool((rs[:, 1:25] <= rs[:, :24]).all())                                           # new order
+    want = fp32_pair_scores(torch.arange(nq, device=cuda_device), ri[:, :25])
+    assert torch.allclose(rs[:, :25], want, rtol=1e-6)
+    # reversing scorer: the head comes out reversed
+    rs2, ri2 = rir.rerank_topk(sc, ix, lambda q, c: -sc[:, :c.shape[1]], top_r=k)
+    assert torch.equal(ri2, torch.flip(ix, dims=[1]))
+    with pytest.raises(ValueError):
+        rir.rerank_topk(sc, ix, lambda q, c: torch.zeros(1, device=cuda_device))
