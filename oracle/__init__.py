@@ -12,5 +12,8 @@ Pinning ("is the oracle itself right?"):
     `tests/golden/` — the fixtures travel to the GPU box where /root/reference does not exist;
   * the reference has NO tests or golden vectors of its own for this path, and NO implementation of
     top-k truncation semantics, alpha query expansion or the sharded merge: for those three the oracle is a
-    restatement of the published formula only ("parity unpinned").
+    restatement of the published formula only ("parity unpinned", see DESIGN.md §3);
+  * `oracle/topk_logic.py` is not an oracle of the reference at all: it emulates the ranking-key / fused-threshold /
+    first-phase-redo LOGIC of the tcgen05 scan in numpy, so that the exactness argument is property-tested on the CPU
+    (`tests/test_topk_logic.py`).
 """
