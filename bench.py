@@ -142,14 +142,14 @@ def cpu_reference_step_time(nq: int, n_sample: int, d: int, reps: int, warm: int
     for i in range(warm + reps):
         t0 = time.perf_counter()
         sim = S.similarity(Q, X).numpy()
-        ranks = np.argsort(-sim, axis=1)
         t1 = time.perf_counter()
-        sc, ix = torch.topk(torch.from_numpy(sim), k=min(TOPK, n_sample), dim=-1)
+        ranks = np.argsort(-sim, axis=1)
         t2 = time.perf_counter()
+        sc, ix = torch.topk(torch.from_numpy(sim), k=min(TOPK, n_sample), dim=-1)
+        t3 = time.perf_counter()
         if i >= warm:
-            times.append(t1 - t0)
-            times_topk.append((t1 - t0) - 0.0 + 0.0)  # placeholder to keep lists aligned
-            times_topk[-1] = (t2 - t1)
+            times.append(t2 - t0)                    # mm + full argsort: what the reference does
+            times_topk.append((t1 - t0) + (t3 - t2))  # mm + torch.topk: the "strong CPU" variant
         del ranks, sc, ix
     return times, times_topk
 
@@ -381,7 +381,7 @@ def run_ours(args):
                 "value": args.nq / t_full, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                 "sample": f"fp32 torch.mm + np.argsort(-sim,1) (iris_evaluate.py:383-386) on {args.nq} queries x {n_sample} rows, "
                           f"best of 5, time scaled x{scale:.3f} (linear in rows) to {args.n} rows",
-                "topk_variant_value": args.nq / ((min(times) - 0 + min(times_topk)) * scale) if times_topk else None,
+                "topk_variant_value": args.nq / (min(times_topk) * scale) if times_topk else None,  # mm + torch.topk
             }
         print(json.dumps(line))
     if world > 1:

@@ -103,7 +103,7 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
   size_t o = 0;
   pl->off_tau_s = o; o = align_up(o + g * 4, 256);
   pl->off_tau_i = o; o = align_up(o + g * 4, 256);
-  pl->off_cnt = o;   o = align_up(o + 2 * g * 4 + 64, 256);  // cnt | grid-barrier counters | tau flags (one memset)
+  pl->off_cnt = o;   o = align_up(o + g * 4 + 64, 256);  // cnt | grid-barrier counter (one memset)
   pl->off_ovf = o;   o = align_up(o + g * 4, 256);
   pl->off_sample = o; o = align_up(o + g * (size_t)pl->sblk * kSampleBlockRows * 4, 256);
   pl->off_cand = o;  o = align_up(o + g * (size_t)pl->cap * 8, 256);
@@ -255,7 +255,6 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
       p.ex.q_base = g0;
     }
     p.gbar = p.cnt + align_up((size_t)pl.group, 128);  // right behind cnt[]
-    p.tau_flag = p.gbar + 16;
     if (pl.scan_all) {
       // every row is a candidate: slot == row, cnt = n set by the select kernel's launch parameters
       if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));

@@ -84,8 +84,8 @@ struct SimParams {
   // best kFusedTopT keys per query of its first tile(s) in sample_keys, a grid barrier follows, tau is computed by the
   // scan kernel and the remaining rounds filter with it.  Tiles are visited in a multiplicative permutation so the
   // first `fused_tiles` of them are spread over the whole shard.
-  uint32_t* gbar;        // [2] grid-barrier counters (zeroed by the host before the launch)
-  uint32_t* tau_flag;    // (unused: tau_score[q] carries its own "published" sentinel, kTauUnset)
+  uint32_t* gbar;        // grid-barrier counter (zeroed by the host before the launch); tau_score[q] is preset to
+                         // kTauUnset and carries its own "published" state
   int fused_tiles;       // first-phase tiles == slots per query in sample_keys / kFusedTopT
   long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
   long long perm_n;      // number of database tiles
