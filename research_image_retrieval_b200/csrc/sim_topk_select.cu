@@ -4,12 +4,27 @@
 // Replaces np.argsort(-similarity, axis=1) (iris_evaluate.py:386) / torch.topk(similarity, k)
 // (reference/manus/7_AdaptiveHybridModel/modified/adaptive_hybrid_retrieval_complete.py:428): the [nq, n] matrix is
 // never sorted; only the candidates that survive the per-query threshold are.
+#include <stdlib.h>
 #include "sim_topk.cuh"
 #include "topk_select.cuh"
 
 namespace rir {
 
-constexpr int kSelectThreads = 512;
+constexpr int kSelectThreads = 512;  // upper bound (launch bounds, shared-memory sizing)
+
+// threads per query CTA of the select / merge kernels (development override RIR_SELECT_THREADS; measured per-step
+// overhead beyond the scan, 70 queries: 512 threads 28.4 us, 256 threads 31.7 us, 128 threads 38.3 us)
+static int select_threads() {
+  static int n = 0;
+  if (n == 0) {
+    n = 512;
+    if (const char* e = getenv("RIR_SELECT_THREADS")) {
+      const int v = atoi(e);
+      if (v == 128 || v == 256 || v == 512) n = v;
+    }
+  }
+  return n;
+}
 
 // ---------------------------------------------------------------------------------------------
 // tau[q] = k-th best key of the dense sample scores
@@ -391,13 +406,13 @@ int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long
   }
   if (dtype == RIR_BF16) {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_BF16><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    final_select_kernel<RIR_BF16><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
   } else if (dtype == RIR_FP8E4M3) {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_FP8E4M3><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    final_select_kernel<RIR_FP8E4M3><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
   } else {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_F32><<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    final_select_kernel<RIR_F32><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
   }
   RIR_LAUNCH_OK();
   return RIR_OK;
@@ -556,7 +571,7 @@ int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, i
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
   const size_t smem = (size_t)kpad * sizeof(uint64_t);
   RIR_CUDA_OK(cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_exchange_kernel<<<nq, kSelectThreads, smem, st>>>(ex, k, kpad, out_score, out_idx);
+  merge_exchange_kernel<<<nq, select_threads(), smem, st>>>(ex, k, kpad, out_score, out_idx);
   RIR_LAUNCH_OK();
   return RIR_OK;
 }
