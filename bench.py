@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1], "RParis6k-shape with 1M distractors"): 70 queries x 1,007,323 database rows x
 2048-d bf16, exact top-100; the database is row-sharded over the N GPUs (strong scaling: total work is fixed).
 One step = one 70-query batch through the whole search path:
-    sample pass -> per-query threshold -> full scan (tcgen05, TMA) -> exact select [-> NCCL all-gather -> merge].
+    fused tcgen05 scan (first round = sample, in-kernel threshold) -> exact select [-> NVLink peer exchange -> merge].
 `value` = queries/s with the query batch already packed in HBM; `e2e` = the same through the host-facing call:
 pinned fp32 host queries -> H2D -> bf16 pack -> search -> D2H of (scores, idx), database resident.
 Prints ONE JSON line on rank 0.
@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--no-parity", action="store_true")   # skip the in-process parity block
+    ap.add_argument("--no-extras", action="store_true")   # skip the 1-query / 1024-query points
     return ap.parse_args()
 
 
@@ -126,53 +128,75 @@ def make_queries_fp32(nq: int, d: int):
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU path, restated in oracle/ (the reference is pure Python: no _ref build)
+# reference arm: the reference's own CPU path (iris_evaluate.py:383-386), on the FULL configuration
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_step_time(nq: int, n_sample: int, d: int, reps: int, warm: int):
-    """iris_evaluate.py:383-386 as written — fp32 torch.mm + np.argsort(-sim, axis=1) — on a bounded row sample."""
+def make_rows_cpu_fp32(n: int, d: int):
+    """n unit-norm fp32 rows in host memory, generated chunk-wise on all cores (numpy releases the GIL)."""
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    out = np.empty((n, d), dtype=np.float32)
+
+    def fill(c):
+        a, b = c * CHUNK, min(n, (c + 1) * CHUNK)
+        blk = np.random.default_rng(SEED * 100003 + c).standard_normal((b - a, d), dtype=np.float32)
+        blk /= np.linalg.norm(blk, axis=1, keepdims=True)
+        out[a:b] = blk
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        list(ex.map(fill, range(-(-n // CHUNK))))
+    return torch.from_numpy(out)
+
+
+def cpu_reference_steps(nq: int, n: int, d: int, k: int, reps: int, warm: int, topk_variant: bool = True):
+    """The reference's similarity + ranking exactly as written — fp32 `torch.mm(q, g.t())` then
+    `np.argsort(-similarity, axis=1)` (iris_evaluate.py:383-386, restated in oracle/search_oracle.py) — on ALL n rows,
+    with every host core torch / numpy will use.  Returns (per-step seconds, seconds of the mm + torch.topk variant)."""
     import numpy as np
     import torch
     from oracle import search_oracle as S
     torch.set_num_threads(os.cpu_count() or 1)
-    gen = torch.Generator().manual_seed(SEED)
-    X = torch.randn(n_sample, d, generator=gen)
-    X /= X.norm(dim=1, keepdim=True)
+    X = make_rows_cpu_fp32(n, d)
     Q = make_queries_fp32(nq, d)
-    times, times_topk = [], []
+    times = []
     for i in range(warm + reps):
         t0 = time.perf_counter()
         sim = S.similarity(Q, X).numpy()
-        t1 = time.perf_counter()
         ranks = np.argsort(-sim, axis=1)
-        t2 = time.perf_counter()
-        sc, ix = torch.topk(torch.from_numpy(sim), k=min(TOPK, n_sample), dim=-1)
-        t3 = time.perf_counter()
+        t1 = time.perf_counter()
         if i >= warm:
-            times.append(t2 - t0)                    # mm + full argsort: what the reference does
-            times_topk.append((t1 - t0) + (t3 - t2))  # mm + torch.topk: the "strong CPU" variant (BASELINE.md §3)
-        del ranks, sc, ix
-    return times, times_topk
+            times.append(t1 - t0)
+        del ranks
+    t_topk = None
+    if topk_variant:  # the "strong CPU" variant (BASELINE.md §3): mm + torch.topk(k) instead of the full argsort
+        t0 = time.perf_counter()
+        sim = S.similarity(Q, X)
+        sc, ix = torch.topk(sim, k=min(k, n), dim=-1)
+        t_topk = time.perf_counter() - t0
+        del sc, ix
+    return times, t_topk
+
+
+def cpu_sample_text(args):
+    return (f"fp32 torch.mm + np.argsort(-sim, axis=1) (iris_evaluate.py:383-386) on the full configuration: "
+            f"{args.nq} queries x {args.n} rows x {args.d}-d per step, {os.cpu_count() or 1} host threads")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = min(args.n, 131072)
-    scale = args.n / n_sample
-    times, _ = cpu_reference_step_time(args.nq, n_sample, args.d, args.steps, args.warmup)
-    total = sum(times)
-    per_step_full = total / len(times) * scale
-    value = args.nq / per_step_full
+    times, t_topk = cpu_reference_steps(args.nq, args.n, args.d, args.k, max(args.steps, 1), args.warmup)
+    per_step = sum(times) / len(times)
+    value = args.nq / per_step
     cores = os.cpu_count() or 1
     line = {
-        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, extra={"cpu_sample_rows": n_sample}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"fp32 torch.mm + np.argsort(-sim,1) (iris_evaluate.py:383-386) on {args.nq} queries x "
-                                   f"{n_sample} rows per step, time scaled x{scale:.3f} (linear in rows) to {args.n} rows"},
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "step_ms": step_stats([t * 1e3 for t in times]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(args),
+                         "topk_variant_value": (args.nq / t_topk) if t_topk else None},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -185,25 +209,55 @@ def metric_name(args):
             "(development override of the BASELINE workload)")
 
 
-def workload_config(args, extra=None):
-    c = {"workload": f"BASELINE configs[1]: {args.nq} queries x {args.n} db rows x {args.d}-d {args.dtype}, exact top-{args.k}, "
-                     f"db row-sharded over {args.gpus} GPU(s)",
-         "nq": args.nq, "n_db": args.n, "dim": args.d, "k": args.k, "parallelism": f"db-shard x{args.gpus}",
-         "l2_note": "per-GPU shard (>= 516 MB) exceeds the 126 MB L2, so every step re-reads it from HBM; no explicit flush"}
-    if extra:
-        c.update(extra)
-    return c
+def workload_config(args):
+    """Identical in both arms (the driver compares the dicts): only what defines the workload."""
+    default = (args.nq, args.n, args.d, args.k, args.dtype) == (NQ, N_DB, DIM, TOPK, "bf16")
+    name = "BASELINE configs[1] (RParis6k-shape + 1M distractors)" if default else "development override"
+    return {"workload": f"{name}: {args.nq} queries x {args.n} db rows x {args.d}-d {args.dtype}, exact top-{args.k}, "
+                        f"db row-sharded over {args.gpus} GPU(s)",
+            "nq": args.nq, "n_db": args.n, "dim": args.d, "k": args.k, "parallelism": f"db-shard x{args.gpus}",
+            "l2_note": "per-GPU shard (>= 516 MB) exceeds the 126 MB L2, so every step re-reads it from HBM; no explicit flush"}
+
+
+def step_stats(ms_list):
+    s = sorted(ms_list)
+    if not s:
+        return None
+    return {"min": s[0], "median": s[len(s) // 2], "max": s[-1], "n": len(s)}
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def tie_aware_mismatch(got_sc, got_ix, ref_sc, ref_ix, eps):
+    """Two top-k lists of the same queries, both sorted by (score desc, index asc), scored by different arithmetic
+    (tensor-core vs CUDA-core accumulation order).  They must agree position by position in score (relative eps) and
+    in index wherever the neighbouring scores are further apart than eps.  Returns (ok, #index differences inside
+    ties, message)."""
+    import numpy as np
+    tol = eps * np.maximum(np.abs(ref_sc), 1e-6)
+    if got_sc.shape != ref_sc.shape or not np.all(np.abs(got_sc - ref_sc) <= tol):
+        bad = np.argwhere(~(np.abs(got_sc - ref_sc) <= tol))[:3].tolist() if got_sc.shape == ref_sc.shape else "shape"
+        return False, 0, f"scores differ beyond {eps} relative at {bad}"
+    diff = got_ix != ref_ix
+    n_tie = int(diff.sum())
+    for q, j in np.argwhere(diff):
+        # a differing index is only acceptable when `ref` holds another row within eps of this score (a tie)
+        near = np.abs(ref_sc[q] - got_sc[q, j]) <= 2 * tol[q, j]
+        if near.sum() < 2 and not (j == got_sc.shape[1] - 1):
+            return False, n_tie, f"query {q} position {j}: index {got_ix[q, j]} vs {ref_ix[q, j]} without a tie"
+    return True, n_tie, "ok"
+
+
 def run_ours(args):
+    import ctypes
+
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     import research_image_retrieval_b200 as rir
-    from research_image_retrieval_b200 import _lib
+    from research_image_retrieval_b200 import _lib, search as rsearch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,6 +270,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = rir.load()
     _lib.check(lib.rir_device_check())
+    steps, warmup = max(args.steps, 1), max(args.warmup, 3)
 
     # ---- resident database shard ----
     lo, hi = rir.shard_bounds(args.n, world, rank)
@@ -235,158 +290,233 @@ def run_ours(args):
             scales.append(s)
         db = rir.Database(torch.cat(parts), torch.cat(scales), "fp8", idx_offset=lo)
     sdb = rir.ShardedDatabase(db)
+    extras_on = not args.no_extras and args.nq == NQ
     exchange = "none (1 GPU)"
     if world > 1:
         # the one exchange step of the sharded search: NVLink peer-memory stores from the select kernel + a waiting
         # merge kernel (rir_sim_topk_sharded); --exchange nccl keeps the all-gather + merge path
         exchange = "nccl all-gather + merge kernel"
-        if args.exchange == "peer" and sdb.enable_peer_exchange(args.nq, args.k):
+        if args.exchange == "peer" and sdb.enable_peer_exchange(max(args.nq, 1024 if extras_on else 1), args.k):
             exchange = "nvlink peer-memory stores + waiting merge kernel (no collective call)"
-    q_host = make_queries_fp32(args.nq, args.d).pin_memory()
-    qr, qs = db.pack_queries(q_host.to(dev))
     k = args.k
     esz = 2 if args.dtype == "bf16" else 1
-
-    # scan-kernel events: rir_sim_topk records (start, stop) around its full-scan launch when armed
-    def step_resident():
-        return sdb.search(qr, qs, k, path=args.path)
-
-    out_host_s = torch.empty((args.nq, k), dtype=torch.float32).pin_memory()
-    out_host_i = torch.empty((args.nq, k), dtype=torch.int32).pin_memory()
-
-    host_call = args.dtype in ("bf16", "fp8") and (world == 1 or exchange.startswith("nvlink"))
-
-    def step_e2e():
-        if host_call:  # ONE C-ABI call on host buffers (rir_search_host) + a stream synchronise
-            return sdb.query_host(q_host, k, out=(out_host_s, out_host_i), path=args.path)
-        qd = q_host.to(dev, non_blocking=True)
-        r, s = db.pack_queries(qd)
-        sc, ix = sdb.search(r, s, k, path=args.path)
-        out_host_s.copy_(sc, non_blocking=True)
-        out_host_i.copy_(ix, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
-        return out_host_s, out_host_i
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, events=None):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            if events is not None:
-                lib.rir_profile_scan_events(events[i][0].cuda_event, events[i][1].cuda_event)
-            fn()
-        if events is not None:
-            lib.rir_profile_scan_events(None, None)
-        e1.record()
-        sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    sampler = ClockSampler(local_rank)
-    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in events:  # materialise the CUDA events before handing raw handles to the C ABI
-        a.record()
-        b.record()
-    sampler.start()
-    ms = timed(step_resident, args.steps, events)
-    clocks = sampler.stop()
-    scan_ms = [a.elapsed_time(b) for a, b in events]
-    scan_avg_ms = sum(scan_ms) / len(scan_ms)
-
-    for _ in range(3):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-
-    value = args.nq * args.steps / (ms * 1e-3)
-    e2e_value = args.nq * args.steps / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel (the scan): algorithmic work / measured launch duration ----
-    # HBM-bound while 2*nq flop per database byte stays under the ridge (~214 flop/B, i.e. nq < ~200 for bf16),
-    # tensor-bound above.
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     except Exception:
         pass
-    stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2 and n_local < 2 * 148 * 256)
-    kernel_name = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
-    traffic = None  # dram bytes of one scan launch from the committed ncu capture of the SAME configuration, else null
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(f"nq{args.nq}")
-        if t and world == 1 and not stream_path and (args.n, args.d, args.dtype) == (N_DB, DIM, "bf16"):
-            traffic = t["dram_bytes_per_launch"]
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bf16_burst = float(peaks.get("bf16_tflops", 1590.0))
+    bf16_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    fp8_peak = None
+    try:  # measured on this pool by tools/measure_fp8_peak.py (an own tcgen05 kind::f8f6f4 loop + torch._scaled_mm)
+        with open(os.path.join(ROOT, "profiles", "fp8_peak.json")) as f:
+            fp8_peak = float(json.load(f)["fp8_tflops"])
     except Exception:
         pass
-    flops = 2.0 * args.nq * n_local * args.d
-    alg_bytes = n_local * args.d * esz + args.nq * args.d * esz
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    if flops / alg_bytes < 214.0:
-        achieved = alg_bytes / (scan_avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "kernel": kernel_name, "kernel_ms": scan_avg_ms,
-                    "algorithmic_bytes_per_launch": alg_bytes,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"}
-    else:
-        tf_peak = float(peaks.get("bf16_tflops", 1590.0)) * (2.0 if args.dtype == "fp8" else 1.0)
-        achieved = flops / (scan_avg_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": traffic, "kernel": kernel_name, "kernel_ms": scan_avg_ms,
-                    "algorithmic_flops_per_launch": flops,
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone (of measured)" if peaks
-                                    else "1590 TFLOP/s (of fallback, B200_PROFILING.md)") +
-                                   (" x2 for fp8" if args.dtype == "fp8" else "")}
 
-    # our kernels per step (memsets are not kernels): fused tcgen05 path = scan + select (which also redoes overflowed
-    # queries itself); the three-launch route adds sample + threshold; tiny shards: scan-all + select
-    if n_local <= 16384:
-        kernels_per_step = 2
-    elif stream_path or n_local < 2 * 148 * 256 or args.k > 592:
-        kernels_per_step = 4
-    else:
-        kernels_per_step = 2
-    kernels_per_step += 1 if world > 1 else 0  # merge
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(nq, n_steps, n_warm, with_e2e):
+        """n_steps timed steps of an nq-query batch: resident (packed queries in HBM) and, optionally, end to end
+        through the host-buffer call.  Device-timed with CUDA events, max over ranks."""
+        q_host = make_queries_fp32(nq, args.d).pin_memory()
+        qr, qs = db.pack_queries(q_host.to(dev))
+        out_s = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        out_i = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        host_call = world == 1 or exchange.startswith("nvlink")
+
+        def step_resident():
+            return sdb.search(qr, qs, k, path=args.path)
+
+        def step_e2e():
+            if host_call:  # ONE C-ABI call on host buffers (rir_search_host) + a stream synchronise
+                return sdb.query_host(q_host, k, out=(out_s, out_i), path=args.path)
+            qd = q_host.to(dev, non_blocking=True)
+            r, s = db.pack_queries(qd)
+            sc, ix = sdb.search(r, s, k, path=args.path)
+            out_s.copy_(sc, non_blocking=True)
+            out_i.copy_(ix, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
+            return out_s, out_i
+
+        def timed(fn, profile_scan):
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+            sync_all()
+            if profile_scan:
+                lib.rir_profile_scan_begin()
+            marks[0].record()
+            for i in range(n_steps):
+                fn()
+                marks[i + 1].record()
+            sync_all()
+            scan = None
+            if profile_scan:
+                cap = 64 * n_steps + 64
+                buf = (ctypes.c_float * cap)()
+                cnt = ctypes.c_int(0)
+                _lib.check(lib.rir_profile_scan_end(buf, cap, ctypes.byref(cnt)))
+                scan = [float(buf[i]) for i in range(min(cnt.value, cap))]
+            ms = marks[0].elapsed_time(marks[-1])
+            per = [marks[i].elapsed_time(marks[i + 1]) for i in range(n_steps)]
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, per, scan
+
+        for _ in range(n_warm):
+            step_resident()
+        ms, per, scan = timed(step_resident, True)
+        res = {"ms": ms, "per_step": per, "scan_ms_per_step": sum(scan) / n_steps if scan else None,
+               "scan_launches_per_step": (len(scan) / n_steps) if scan else 0, "qr": qr, "qs": qs}
+        if with_e2e:
+            for _ in range(3):
+                step_e2e()
+            res["ms_e2e"], res["per_step_e2e"], _ = timed(step_e2e, False)
+        return res
+
+    def kernels_per_step(nq):
+        """Our kernels per resident step (no memsets any more: the select kernel leaves the workspace header clean)."""
+        groups = -(-nq // 4096)
+        if n_local <= 16384:
+            per_group = 2                                   # scan-all + select
+        elif args.path == "stream" or n_local < 2 * 148 * 256 or args.k > 592:
+            per_group = 4                                   # sample, threshold, scan, select
+        else:
+            per_group = 2                                   # fused scan + select
+        return groups * per_group + (1 if world > 1 else 0)  # + exchange merge
+
+    def roofline_of(nq, scan_ms):
+        flops = 2.0 * nq * n_local * args.d
+        alg_bytes = n_local * args.d * esz + nq * args.d * esz
+        if flops / alg_bytes < 214.0:
+            achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"}
+        if args.dtype == "fp8":
+            tf_peak = fp8_peak if fp8_peak else 2.0 * bf16_burst
+            src = ("profiles/fp8_peak.json (of measured, tools/measure_fp8_peak.py)" if fp8_peak
+                   else "2 x MEASURED_PEAKS.json bf16_tflops (assumed: no fp8 measurement committed)")
+        else:
+            tf_peak = bf16_burst
+            src = ("MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone (of measured)" if peaks
+                   else "1590 TFLOP/s (of fallback, B200_PROFILING.md)")
+        achieved = flops / (scan_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "kernel_ms": scan_ms, "algorithmic_flops_per_launch": flops, "peak_source": src}
+
+    # ---- headline: the BASELINE batch ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    head = measure(args.nq, steps, warmup, with_e2e=True)
+    clocks = sampler.stop()
+    value = args.nq * steps / (head["ms"] * 1e-3)
+    e2e_value = args.nq * steps / (head["ms_e2e"] * 1e-3)
+    stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2 and n_local < 2 * 148 * 256)
+    roofline = roofline_of(args.nq, head["scan_ms_per_step"])
+    roofline["kernel"] = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
+    roofline["traffic"] = None  # dram bytes of one scan launch from the committed ncu capture of the SAME configuration
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        t = tj.get(f"nq{args.nq}")
+        if t and world == 1 and not stream_path and (args.n, args.d, args.dtype) == (N_DB, DIM, "bf16"):
+            roofline["traffic"] = t["dram_bytes_per_launch"]
+            roofline["traffic_source"] = f"profiles/traffic.json ({tj.get('captured_at', 'ncu --set full capture')})"
+    except Exception:
+        pass
+
+    # ---- parity, visible to the driver: the timed path against independent implementations, same process ----
+    parity = None
+    if not args.no_parity:
+        nqc = min(8, args.nq)
+        qr, qs = head["qr"], head["qs"]
+        sc_p, ix_p = sdb.search(qr, qs, k, path=args.path)            # the path that was timed
+        peer_eq_nccl = None
+        if world > 1 and exchange.startswith("nvlink"):
+            sc_n, ix_n = sdb.search(qr, qs, k, path=args.path, exchange="nccl")
+            flag = torch.tensor([int(torch.equal(ix_p, ix_n) and torch.equal(sc_p, sc_n))], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            peer_eq_nccl = bool(flag.item())
+        # independent: RIR_PATH_EXACT (one CTA per query, CUDA-core fp32 FMAs, running top-k — shares no scan / select
+        # code with the timed path) on every shard, all-gather, host merge with the order rule (score desc, index asc)
+        k_loc = min(k, n_local)
+        q8 = qr[:nqc].contiguous()
+        s8 = None if qs is None else qs[:nqc].contiguous()
+        sc_x, ix_x = rsearch.sim_topk(q8, db.rows, k_loc, dtype=args.dtype, q_scale=s8, x_scale=db.scale,
+                                      idx_offset=lo, path="exact")
+        sc_x, ix_x = rsearch.pad_topk(sc_x, ix_x, k)
+        if world > 1:
+            all_s, all_i = rsearch.gather_topk(sc_x, ix_x, world)
+        else:
+            all_s, all_i = sc_x[None], ix_x[None]
+        ref_sc, ref_ix = rsearch.merge_topk_host(all_s.cpu().numpy(), all_i.cpu().numpy(), k)
+        ok, n_tie, msg = tie_aware_mismatch(sc_p[:nqc].cpu().numpy(), ix_p[:nqc].cpu().numpy(), ref_sc, ref_ix, 1e-3)
+        flag = torch.tensor([int(ok)], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"peer_eq_nccl": peer_eq_nccl, "vs_exact": "ok" if bool(flag.item()) else f"MISMATCH: {msg}",
+                  "queries": nqc, "index_differences_inside_ties": n_tie, "tolerance": "1e-3 relative (bf16 bar)",
+                  "note": "timed path vs RIR_PATH_EXACT per shard + host merge" +
+                          ("; peer-memory exchange vs NCCL all-gather path bit-identical on all queries" if peer_eq_nccl else "")}
+
+    # ---- the two north-star regimes, same process: 1 query (HBM-bound) and 1024 queries (tensor-bound) ----
+    extras = None
+    if extras_on:
+        extras = {}
+        r1 = measure(1, 20, 3, with_e2e=False)
+        rf = roofline_of(1, r1["scan_ms_per_step"])
+        extras["q1"] = {"value": 1 * 20 / (r1["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r1["ms"] / 20,
+                        "scan_ms": r1["scan_ms_per_step"], "hbm_gbs": rf["achieved"], "hbm_frac": rf["frac"],
+                        "target": "north_star: >= 0.80 of HBM peak at 1 query"}
+        rk = measure(1024, 8, 3, with_e2e=False)
+        rf = roofline_of(1024, rk["scan_ms_per_step"])
+        extras["q1024"] = {"value": 1024 * 8 / (rk["ms"] * 1e-3), "unit": UNIT, "ms_per_step": rk["ms"] / 8,
+                           "scan_ms": rk["scan_ms_per_step"], "tflops": rf["achieved"],
+                           "frac_of_burst": rf["achieved"] / bf16_burst if args.dtype == "bf16" else rf["frac"],
+                           "frac_of_sustained": rf["achieved"] / bf16_sustained if args.dtype == "bf16" else None,
+                           "target": "north_star: >= 0.60 tensor pipe at 1k queries"}
 
     if rank == 0:
         line = {
-            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, {"path": args.path, "exchange": exchange}),
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": head["ms"] / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
+            "impl_detail": {"path": args.path, "exchange": exchange},
+            "step_ms": step_stats(head["per_step"]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.nq * args.d * 4,
-                    "d2h_bytes_per_step": args.nq * k * 8, "ms_per_step": ms_e2e / args.steps,
+                    "d2h_bytes_per_step": args.nq * k * 8, "ms_per_step": head["ms_e2e"] / steps,
+                    "step_ms": step_stats(head["per_step_e2e"]),
+                    "gpu_launches": (kernels_per_step(args.nq) + 1) * steps,
                     "note": "rir_search_host: pinned fp32 host queries -> H2D -> pack -> search -> D2H (scores, idx) -> stream sync, "
                             "every step; database resident"},
-            "gpu_launches": kernels_per_step * args.steps,
+            "gpu_launches": kernels_per_step(args.nq) * steps,
             "roofline": roofline,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if extras is not None:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
-            n_sample = min(args.n, 131072)
-            times, times_topk = cpu_reference_step_time(args.nq, n_sample, args.d, reps=5, warm=1)
-            scale = args.n / n_sample
-            t_full = min(times) * scale
+            times, t_topk = cpu_reference_steps(args.nq, args.n, args.d, args.k, reps=3, warm=1)
             line["cpu_baseline"] = {
-                "value": args.nq / t_full, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                "sample": f"fp32 torch.mm + np.argsort(-sim,1) (iris_evaluate.py:383-386) on {args.nq} queries x {n_sample} rows, "
-                          f"best of 5, time scaled x{scale:.3f} (linear in rows) to {args.n} rows",
-                "topk_variant_value": args.nq / (min(times_topk) * scale) if times_topk else None,  # mm + torch.topk
+                "value": args.nq / min(times), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": cpu_sample_text(args) + ", best of 3 after 1 warm-up",
+                "topk_variant_value": (args.nq / t_topk) if t_topk else None,  # mm + torch.topk
             }
         print(json.dumps(line))
     if world > 1:
         sdb.close()
         dist.destroy_process_group()
+    if parity is not None and (parity["vs_exact"] != "ok" or parity["peer_eq_nccl"] is False):
+        raise SystemExit(3)
 
 
 def main():

@@ -54,6 +54,10 @@ extern "C" {
 #define RIR_PATH_STREAM 1 /* TMA-bulk ring + CUDA-core dot products (tiny query batches) */
 #define RIR_PATH_MMA 2    /* tcgen05 tensor-core contraction, TMEM accumulators          */
 #define RIR_PATH_EXACT 3  /* one-CTA-per-query robust scan (overflow fallback; slow)     */
+/* flag, OR-ed into `path`: the workspace header was initialised with rir_sim_topk_workspace_init and has since been
+ * used only by successful rir_sim_topk / rir_sim_topk_sharded / rir_search_host calls (any shapes) — the search then
+ * issues no memset launches (its select kernel leaves the header initialised for the next call). */
+#define RIR_WS_CLEAN 0x100
 
 /* per-(protocol,query) status written by rir_revisited_map / rir_compute_map */
 #define RIR_MAP_OK 0
@@ -129,10 +133,19 @@ int rir_sim_topk(const void* Q, const void* X, int dtype, const float* q_scale, 
                  int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
                  void* workspace, size_t workspace_bytes, int path, void* stream);
 
-/* Measurement hook (bench.py's roofline): arm a pair of cudaEvent_t handles (passed as void*) that the following
- * rir_sim_topk calls of THIS host thread record immediately before / after their full-scan kernel launch(es) on the
- * call's stream.  Pass NULL, NULL to disarm.  The events must outlive the calls; timing is read by the caller. */
-int rir_profile_scan_events(void* ev_start, void* ev_stop);
+/* One-time initialisation of a search workspace (the first bytes of a rir_sim_topk / rir_search_host workspace are a
+ * fixed-layout header: per-query thresholds, candidate counters, the grid-barrier counter).  Enqueues two memsets on
+ * `stream`.  Calls that pass RIR_WS_CLEAN in `path` rely on it; calls without the flag initialise the header
+ * themselves (two extra launches per search).  Re-initialise after a call that returned an error. */
+int rir_sim_topk_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook (bench.py's roofline).  rir_profile_scan_begin arms THIS host thread: every full-scan kernel
+ * launch of the following rir_sim_topk / _sharded / rir_search_host calls is bracketed by a pair of CUDA events from a
+ * library-owned pool, on the call's stream (a search of more than 4096 queries launches one scan per query group —
+ * each is recorded).  rir_profile_scan_end disarms, synchronises on the recorded events and returns the number of
+ * scan launches since begin in *n_launches and the duration of launch i (milliseconds) in ms_out[i], i < cap. */
+int rir_profile_scan_begin(void);
+int rir_profile_scan_end(float* ms_out, int cap, int* n_launches);
 
 /* Development hook: event timeline of the tcgen05 scan.  dev_buf = device buffer of (1 + 2 * cap_events) uint64, zeroed
  * by the caller; the following rir_sim_topk calls of THIS host thread append (meta, %globaltimer ns) pairs —

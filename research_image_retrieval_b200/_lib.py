@@ -17,6 +17,7 @@ RIR_E_ARG, RIR_E_ARCH, RIR_E_CUDA, RIR_E_WORKSPACE = -1, -2, -3, -4
 RIR_F32, RIR_BF16, RIR_FP8E4M3 = 0, 1, 2
 RIR_POOL_GEM, RIR_POOL_MAX, RIR_POOL_AVG = 0, 1, 2
 RIR_PATH_AUTO, RIR_PATH_STREAM, RIR_PATH_MMA, RIR_PATH_EXACT = 0, 1, 2, 3
+RIR_WS_CLEAN = 0x100
 RIR_MAP_OK, RIR_MAP_EMPTY_OK, RIR_MAP_NO_POS_RETRIEVED = 0, 1, 2
 
 PATHS = {"auto": RIR_PATH_AUTO, "stream": RIR_PATH_STREAM, "mma": RIR_PATH_MMA, "exact": RIR_PATH_EXACT}
@@ -37,7 +38,9 @@ SIGNATURES = {
     "rir_sim_topk_workspace": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
     "rir_sim_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
                              c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "rir_profile_scan_events": (c_int, [c_void_p, c_void_p]),
+    "rir_sim_topk_workspace_init": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "rir_profile_scan_begin": (c_int, []),
+    "rir_profile_scan_end": (c_int, [POINTER(c_float), c_int, POINTER(c_int)]),
     "rir_profile_timeline": (c_int, [c_void_p, c_int]),
     "rir_rescore_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "sim_topk.cuh"
 #include "topk_select.cuh"
 
@@ -47,6 +48,11 @@ int check_arch() {
   return RIR_OK;
 }
 
+bool pdl_enabled() {
+  static const int on = getenv("RIR_PDL") ? atoi(getenv("RIR_PDL")) : 1;
+  return on != 0;
+}
+
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -66,6 +72,14 @@ constexpr int kQueryGroup = 4096;      // queries processed per internal pass (b
 constexpr long long kScanAllMaxRows = 16384;
 constexpr int kMaxKFilter = 8192;
 constexpr int kMaxK = 16384;
+
+// fixed workspace header (bytes): tau_score[4096] | tau_idx[4096] | cnt[4096] + barrier counter | ovf[4096]
+constexpr size_t kHdrTauS = 0;
+constexpr size_t kHdrTauI = kHdrTauS + (size_t)kQueryGroup * 4;
+constexpr size_t kHdrCnt = kHdrTauI + (size_t)kQueryGroup * 4;
+constexpr size_t kHdrGbar = kHdrCnt + (size_t)kQueryGroup * 4;  // 256 bytes: the grid-barrier counter
+constexpr size_t kHdrOvf = kHdrGbar + 256;
+constexpr size_t kHdrBytes = kHdrOvf + (size_t)kQueryGroup * 4;
 
 struct SimPlan {
   bool scan_all;
@@ -99,12 +113,15 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
     if (cap < 2048) cap = 2048;
     pl->cap = (int)cap;
   }
+  // The header (tau | cnt | grid-barrier counter | overflow flags) has a FIXED layout, sized for a full query group
+  // whatever nq is: rir_sim_topk_workspace_init establishes "cnt = 0, barrier = 0, tau_score = sentinel" once and the
+  // select kernel restores it at the end of every search, for every shape that re-uses the workspace.
   const size_t g = (size_t)align_up((size_t)pl->group, 128);
-  size_t o = 0;
-  pl->off_tau_s = o; o = align_up(o + g * 4, 256);
-  pl->off_tau_i = o; o = align_up(o + g * 4, 256);
-  pl->off_cnt = o;   o = align_up(o + g * 4 + 64, 256);  // cnt | grid-barrier counter (one memset)
-  pl->off_ovf = o;   o = align_up(o + g * 4, 256);
+  pl->off_tau_s = kHdrTauS;
+  pl->off_tau_i = kHdrTauI;
+  pl->off_cnt = kHdrCnt;
+  pl->off_ovf = kHdrOvf;
+  size_t o = kHdrBytes;
   pl->off_sample = o; o = align_up(o + g * (size_t)pl->sblk * kSampleBlockRows * 4, 256);
   pl->off_cand = o;  o = align_up(o + g * (size_t)pl->cap * 8, 256);
   pl->total = o;
@@ -115,12 +132,48 @@ static bool make_plan(int nq, long long n, int k, SimPlan* pl) {
 
 using namespace rir;
 
-// optional profiling hook: CUDA events recorded around the full-scan launch of the next rir_sim_topk calls
-static thread_local cudaEvent_t g_ev_scan_start = nullptr, g_ev_scan_stop = nullptr;
+// optional profiling hook (bench.py's roofline): while armed, every full-scan launch of THIS host thread is bracketed
+// by a pair of CUDA events from an internal pool — one pair per launch, so searches that run as several query groups
+// (nq > 4096) are measured completely.
+struct ScanEventPool {
+  bool armed = false;
+  std::vector<cudaEvent_t> ev;  // pairs: ev[2i] start, ev[2i+1] stop
+  size_t used = 0;              // events handed out since rir_profile_scan_begin
+};
+static thread_local ScanEventPool g_scan_ev;
 
-extern "C" int rir_profile_scan_events(void* ev_start, void* ev_stop) {
-  g_ev_scan_start = (cudaEvent_t)ev_start;
-  g_ev_scan_stop = (cudaEvent_t)ev_stop;
+static cudaEvent_t scan_event_next() {
+  ScanEventPool& P = g_scan_ev;
+  if (!P.armed) return nullptr;
+  if (P.used == P.ev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    P.ev.push_back(e);
+  }
+  return P.ev[P.used++];
+}
+
+extern "C" int rir_profile_scan_begin(void) {
+  g_scan_ev.armed = true;
+  g_scan_ev.used = 0;
+  return RIR_OK;
+}
+
+extern "C" int rir_profile_scan_end(float* ms_out, int cap, int* n_launches) {
+  ScanEventPool& P = g_scan_ev;
+  P.armed = false;
+  const size_t pairs = P.used / 2;
+  if (n_launches) *n_launches = (int)pairs;
+  for (size_t i = 0; i < pairs; ++i) {
+    RIR_CUDA_OK(cudaEventSynchronize(P.ev[2 * i + 1]));
+    float ms = 0.f;
+    RIR_CUDA_OK(cudaEventElapsedTime(&ms, P.ev[2 * i], P.ev[2 * i + 1]));
+    if (ms_out && (int)i < cap) ms_out[i] = ms;
+  }
+  P.used = 0;
   return RIR_OK;
 }
 
@@ -149,10 +202,25 @@ extern "C" size_t rir_sim_topk_workspace(int nq, int64_t n_local, int d, int k, 
   return pl.total;
 }
 
+extern "C" int rir_sim_topk_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_arch()) return e;
+  RIR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "workspace_init: workspace must be non-null and 256-byte aligned");
+  RIR_REQUIRE(workspace_bytes >= kHdrBytes, "workspace_init: workspace of %zu B is smaller than its %zu B header",
+              workspace_bytes, kHdrBytes);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  RIR_CUDA_OK(cudaMemsetAsync(ws + kHdrTauS, 0xFF, (size_t)kQueryGroup * 4, st));              // kTauUnset
+  RIR_CUDA_OK(cudaMemsetAsync(ws + kHdrCnt, 0, kHdrBytes - kHdrCnt, st));                      // cnt | barrier | ovf
+  return RIR_OK;
+}
+
 static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
                          int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
                          void* workspace, size_t workspace_bytes, int path, void* stream, const Exchange* ex) {
   if (int e = check_arch()) return e;
+  const bool ws_clean = (path & RIR_WS_CLEAN) != 0;  // the caller keeps the header invariant: no memset launches
+  path &= ~RIR_WS_CLEAN;
   const int esz = elem_size(dtype);
   RIR_REQUIRE(esz != 0, "sim_topk: dtype must be RIR_F32, RIR_BF16 or RIR_FP8E4M3 (got %d)", dtype);
   RIR_REQUIRE(dtype != RIR_F32 || path != RIR_PATH_MMA, "sim_topk: fp32 descriptors run on the stream path only");
@@ -254,25 +322,46 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
       p.ex = *ex;
       p.ex.q_base = g0;
     }
-    p.gbar = p.cnt + align_up((size_t)pl.group, 128);  // right behind cnt[]
+    p.gbar = reinterpret_cast<uint32_t*>(ws + kHdrGbar);
+    auto scan_mark = [&]() -> int {  // one event of the armed profiling pool (no-op otherwise)
+      if (cudaEvent_t e = scan_event_next()) RIR_CUDA_OK(cudaEventRecord(e, st));
+      return RIR_OK;
+    };
+    // The header invariant (cnt = 0, barrier = 0, tau_score = sentinel) is restored by the select kernel at the end
+    // of every search; a caller that initialised the workspace once (rir_sim_topk_workspace_init) and says so with
+    // RIR_WS_CLEAN skips these launches.  The first group of a plain call establishes it here.
+    if (!ws_clean && g0 == 0 && !pl.scan_all) {
+      RIR_CUDA_OK(cudaMemsetAsync(ws + kHdrCnt, 0, kHdrOvf - kHdrCnt, st));
+      RIR_CUDA_OK(cudaMemsetAsync(ws + kHdrTauS, 0xFF, (size_t)pl.group * sizeof(float), st));
+    }
+    bool done = false;
     if (pl.scan_all) {
       // every row is a candidate: slot == row, cnt = n set by the select kernel's launch parameters
-      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
+      if (int e = scan_mark()) return e;
       if (int e = run_pass(kModeScanAll)) return e;
-      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
+      if (int e = scan_mark()) return e;
       p.mode = kModeScanAll;
+      done = true;
     } else if (!use_stream && mma_can_fuse(gq, n_local, k)) {
       // ONE launch: the first round of the scan is the sample, tau is derived inside the kernel (sim_topk_mma.cu)
-      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (align_up((size_t)pl.group, 128) + 16) * sizeof(uint32_t), st));
-      RIR_CUDA_OK(cudaMemsetAsync(p.tau_score, 0xFF, (size_t)gq * sizeof(float), st));  // kTauUnset
-      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
-      if (int e = run_pass(kModeFused)) return e;
-      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
-      p.mode = kModeFused;
-    } else {
+      if (int e = scan_mark()) return e;
+      const int e = run_pass(kModeFused);
+      if (e == RIR_OK) {
+        if (int e2 = scan_mark()) return e2;
+        p.mode = kModeFused;
+        done = true;
+      } else if (e != RIR_E_NOFUSE) {
+        return e;
+      } else if (g_scan_ev.armed && g_scan_ev.used > 0) {
+        --g_scan_ev.used;  // the cooperative launch was refused: take the three-launch route below
+      }
+    }
+    if (!done) {
       // what the sample pass keeps: best key per consumer warp (stream) / best T keys per sample tile (tcgen05);
       // >= 2k kept keys per query keep tau tight; very large k falls back to the dense sample
       const int sms = sm_count();
+      p.topt = 0;
+      p.sample_m = 0;
       if (use_stream) {
         if (2 * k <= sms * 8 && (size_t)sms * 8 * 8 <= (size_t)pl.sblk * kSampleBlockRows * 4) {
           p.topt = 1;
@@ -289,10 +378,9 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
       }
       if (int e = run_pass(kModeSample)) return e;
       if (int e = launch_sample_threshold(p, gq, k, st)) return e;
-      RIR_CUDA_OK(cudaMemsetAsync(p.cnt, 0, (size_t)gq * sizeof(uint32_t), st));
-      if (g_ev_scan_start) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_start, st));
+      if (int e = scan_mark()) return e;
       if (int e = run_pass(kModeScanFilter)) return e;
-      if (g_ev_scan_stop) RIR_CUDA_OK(cudaEventRecord(g_ev_scan_stop, st));
+      if (int e = scan_mark()) return e;
       p.mode = kModeScanFilter;
     }
     float* os = out_score + (size_t)g0 * k;

@@ -46,6 +46,27 @@ int sm_count();
     }                                                                                       \
   } while (0)
 
+// Launch with programmatic stream serialization (PDL) unless RIR_PDL=0: the kernel's CTAs may be scheduled while the
+// previous kernel of the stream drains; the kernel itself calls pdl_wait() before touching global memory.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // ranking keys
 // ---------------------------------------------------------------------------------------------
@@ -311,6 +332,15 @@ __device__ __forceinline__ uint32_t tmem_ld_32x32_x1(uint32_t taddr) {
   return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start before the previous kernel of
+// the stream has finished.  pdl_wait() blocks until that kernel has COMPLETED and its memory is visible; every PDL
+// kernel of this library executes it (all threads, unconditionally) before its first global-memory access, so
+// completion stays transitive along the stream.  pdl_launch_dependents() lets the next kernel's CTAs be scheduled as
+// soon as resources free up.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- misc ----
 __device__ __forceinline__ uint4 ldg_stream_16B(const void* p) {

@@ -113,6 +113,8 @@ __device__ __forceinline__ bool passes(float score, uint32_t idx, float ts, uint
 }
 #endif
 
+constexpr int RIR_E_NOFUSE = -100;  // internal: the fused one-launch scan is unavailable, take the three-launch route
+
 // kernels' host launchers (defined in the .cu files)
 int launch_sim_stream(const SimParams& p, int dtype, cudaStream_t st);
 // fills p.topt / sample_m / fused_tiles / perm_* when p.mode == kModeFused

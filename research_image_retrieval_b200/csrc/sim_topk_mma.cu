@@ -43,6 +43,7 @@
 // The first-phase keys are merged into the candidate list by final_select_kernel (sim_topk_select.cu).
 #include <cuda.h>
 #include <stdlib.h>
+#include <atomic>
 #include "sim_topk.cuh"
 
 namespace rir {
@@ -318,6 +319,10 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   if (g.csize > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  // PDL: everything above overlapped the tail of the previous kernel of the stream (the previous search's select /
+  // merge, or the query pack); from here on its results (packed queries, clean workspace header) are visible.
+  pdl_wait();
+  pdl_launch_dependents();  // the select kernel's CTAs move in as this kernel's CTAs retire
   if (threadIdx.x == 0) tl_mark(p, 0, 0);
 
   // virtual tile -> first database row.  Dummy tiles (v >= ntiles) start past the last row (all-OOB loads).
@@ -841,6 +846,16 @@ static long long gcd_ll(long long a, long long b) {
   return a;
 }
 
+// Launch attributes of the scan.  The FUSED scan spins on a grid barrier, so all its CTAs must be co-resident: it is
+// launched with cudaLaunchAttributeCooperative — a grid that cannot be fully resident (another search running on a
+// second stream, a foreign kernel holding SMs) waits at the launch instead of dead-locking inside the barrier.  PDL
+// (programmatic stream serialization) lets the kernel's prologue overlap the previous kernel's tail.  Which
+// combinations the driver accepts together with the cluster attribute is probed once per process: mode 3 =
+// cooperative + PDL, 2 = cooperative only, 1 = neither accepted -> the fused route is disabled and the three-launch
+// route (no in-kernel grid barrier) is used instead.
+static std::atomic<int> g_fused_launch_mode{0};  // 0 = not probed yet
+bool mma_fused_disabled() { return g_fused_launch_mode == 1; }
+
 template <int DT, int MB, int TWO>
 static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
                         unsigned grid, cudaStream_t st) {
@@ -851,18 +866,72 @@ static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap&
   cfg.blockDim = dim3(128 + 128 * MB);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)g.csize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<DT, MB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem_bytes));
-  RIR_CUDA_OK(cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB, TWO>, p, g, tmQ, tmX));
-  RIR_LAUNCH_OK();
-  return RIR_OK;
+  auto launch_with = [&](bool coop, bool pdl) -> cudaError_t {
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)g.csize;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (coop) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    if (pdl && pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB, TWO>, p, g, tmQ, tmX);
+  };
+  if (!g.fused) {
+    RIR_CUDA_OK(launch_with(false, true));
+    RIR_LAUNCH_OK();
+    return RIR_OK;
+  }
+  static const int forced = env_int("RIR_FUSED_LAUNCH_MODE", 0);  // development override: 2, 3, or 4 = no cooperative
+  if (forced == 4) {
+    RIR_CUDA_OK(launch_with(false, true));
+    RIR_LAUNCH_OK();
+    return RIR_OK;
+  }
+  if (g_fused_launch_mode == 0 && forced >= 2 && forced <= 3) g_fused_launch_mode = forced;
+  if (g_fused_launch_mode == 0 || g_fused_launch_mode == 3) {
+    const cudaError_t e = launch_with(true, true);
+    if (e == cudaSuccess) {
+      g_fused_launch_mode = 3;
+      RIR_LAUNCH_OK();
+      return RIR_OK;
+    }
+    cudaGetLastError();
+    if (g_fused_launch_mode == 3) {
+      set_error("fused scan: cooperative launch failed: %s", cudaGetErrorString(e));
+      return RIR_E_CUDA;
+    }
+  }
+  if (g_fused_launch_mode == 0 || g_fused_launch_mode == 2) {
+    const cudaError_t e = launch_with(true, false);
+    if (e == cudaSuccess) {
+      g_fused_launch_mode = 2;
+      RIR_LAUNCH_OK();
+      return RIR_OK;
+    }
+    cudaGetLastError();
+    if (g_fused_launch_mode == 2) {
+      set_error("fused scan: cooperative launch failed: %s", cudaGetErrorString(e));
+      return RIR_E_CUDA;
+    }
+    set_error("fused scan: the driver rejects a cooperative launch of %u CTAs in clusters of %d (%s); "
+              "using the three-launch route", grid, g.csize, cudaGetErrorString(e));
+  }
+  g_fused_launch_mode = 1;
+  return RIR_E_NOFUSE;
 }
 
 template <int DT>
@@ -949,7 +1018,7 @@ static MmaShape plan_shape(int nq) {
 }
 
 bool mma_can_fuse(int nq, long long n, int k) {
-  if (env_int("RIR_MMA_FUSED", 1) == 0) return false;
+  if (env_int("RIR_MMA_FUSED", 1) == 0 || mma_fused_disabled()) return false;
   const MmaShape h = plan_shape(nq);
   const long long ntiles = (n + kTileN - 1) / kTileN;
   // the first phase (one tile per CTA and query) must hold >= 2k keys and be a small part of the scan

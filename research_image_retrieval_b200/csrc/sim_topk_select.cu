@@ -268,19 +268,21 @@ __device__ void exact_scan_body(const SimParams& p, int q, int k, int bufcap, ui
   else write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
 }
 
-constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the radix passes do not re-read L2
+constexpr int kMergeStage = 8192;  // G*k keys the exchange merge stages in shared memory (64 KB)
+constexpr int kStageKeys = 8192;  // candidates staged in shared memory (64 KB) so the select passes do not re-read L2
 constexpr int kMaxRedo = 64;      // first-phase tiles per query that may need a re-score before the exact path takes over
 
 // Fused scan: the first-phase tiles left only their best kFusedTopT keys per query (sample_keys).  Keys >= tau join
-// the candidate list here.  A tile whose LAST kept key still passes tau may hold more passing rows than were kept:
-// it is re-scored with CUDA-core dot products (rare: P[>= 8 of 256 rows above the ~k/148-per-tile rate]).
+// the candidate list here (`list`, holding `*m_io` keys, room for `limit`; shared or global memory).  A tile whose
+// LAST kept key still passes tau may hold more passing rows than were kept: it is re-scored with CUDA-core dot
+// products (rare: P[>= 8 of 256 rows above the ~k/148-per-tile rate]).  Returns false when the query must be redone
+// exactly (too many such tiles, or the list ran out of room).
 template <int DT>
-__device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uint32_t* cnt_io, float* qs,
-                                                  uint32_t* s_extra, int* s_nredo, int* s_redo) {
-  const float ts = p.tau_score[q];
+__device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, float ts, unsigned long long* list,
+                                                  uint32_t limit, uint32_t* m_io, float* qs, uint32_t* s_extra,
+                                                  int* s_nredo, int* s_redo) {
   const unsigned long long* keys = p.sample_keys + (size_t)q * p.sample_m;
-  unsigned long long* c = p.cand + (size_t)q * p.cap;
-  const uint32_t cnt = *cnt_io;
+  const uint32_t cnt = *m_io;
   const int T = p.topt, slots = p.fused_tiles;
   if (threadIdx.x == 0) {
     *s_extra = 0u;
@@ -290,7 +292,7 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
   for (int s = threadIdx.x; s < slots; s += blockDim.x) {
     unsigned long long kk[kFusedTopT];  // the slot's keys in one round of independent loads (T == kFusedTopT)
 #pragma unroll
-    for (int i = 0; i < kFusedTopT; ++i) kk[i] = i < T ? keys[(size_t)s * T + i] : 0ull;
+    for (int i = 0; i < kFusedTopT; ++i) kk[i] = i < T ? __ldcg(keys + (size_t)s * T + i) : 0ull;
     unsigned long long last = kk[0];
 #pragma unroll
     for (int i = 1; i < kFusedTopT; ++i)
@@ -304,7 +306,7 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
         const unsigned long long key = kk[i];
         if (i < T && key != 0ull && key_score(key) >= ts) {
           const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
-          if (pos < (uint32_t)p.cap) c[pos] = key;
+          if (pos < limit) list[pos] = key;
         }
       }
     }
@@ -336,17 +338,20 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, uin
           if (p.x_scale) s *= p.x_scale[base + r];
           if (lane == 0 && s >= ts_lo) {
             const uint32_t pos = cnt + atomicAdd(s_extra, 1u);
-            if (pos < (uint32_t)p.cap) c[pos] = make_key(s, (uint32_t)(base + r));
+            if (pos < limit) list[pos] = make_key(s, (uint32_t)(base + r));
           }
         }
       }
     }
     __syncthreads();
   }
-  *cnt_io = cnt + *s_extra;
-  return true;
+  *m_io = cnt + *s_extra;
+  return *m_io <= limit;
 }
 
+// One CTA per query.  Launched with programmatic stream serialization right behind the scan: the CTAs are scheduled
+// while the scan drains and pass pdl_wait() once it has completed.  The kernel also leaves the workspace header CLEAN
+// for the next search (cnt[q] = 0, tau_score[q] = sentinel, grid-barrier counter = 0): no memset launches per step.
 template <int DT>
 __global__ void __launch_bounds__(kSelectThreads)
     final_select_kernel(const SimParams p, int k, int kpad, long long idx_offset, float* out_score, int32_t* out_idx,
@@ -355,21 +360,44 @@ __global__ void __launch_bounds__(kSelectThreads)
   uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
   uint64_t* stage = dst + kpad;                            // [kStageKeys]
   float* qs = reinterpret_cast<float*>(stage + kStageKeys);  // [d] (first-phase redo / exact redo)
-  __shared__ SelectScratch sc;
-  __shared__ uint32_t s_extra;
+  __shared__ union {
+    SelectScratch sel;
+    BucketScratch bkt;
+  } scr;
+  __shared__ uint32_t s_extra, s_cnt;
+  __shared__ float s_ts;
   __shared__ int s_nredo;
   __shared__ int s_redo[kMaxRedo];
+  pdl_wait();
+  pdl_launch_dependents();
   const int q = blockIdx.x;
-  uint32_t cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : p.cnt[q];  // scan-all: slot == row
-  bool ok = cnt <= (uint32_t)p.cap;
-  if (ok && p.mode == kModeFused) {
-    ok = merge_first_phase<DT>(p, q, &cnt, qs, &s_extra, &s_nredo, s_redo);
-    ok = ok && cnt <= (uint32_t)p.cap;
+  if (threadIdx.x == 0) {
+    s_cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : __ldcg(&p.cnt[q]);  // scan-all: slot == row
+    s_ts = __ldcg(&p.tau_score[q]);
+    // self-cleaning workspace header (rir_sim_topk_workspace_init's invariant)
+    p.cnt[q] = 0u;
+    reinterpret_cast<uint32_t*>(p.tau_score)[q] = kTauUnset;
+    if (q == 0 && p.gbar != nullptr) p.gbar[0] = 0u;
+    ovf[q] = 0u;
   }
+  __syncthreads();
+  uint32_t m = s_cnt;
+  const float ts = s_ts;
+  const unsigned long long* c = p.cand + (size_t)q * p.cap;
+  bool ok = m <= (uint32_t)p.cap;
+  // everything fits in shared memory (the common case): candidates are read from L2 exactly once
+  const uint32_t fp_room = (p.mode == kModeFused) ? (uint32_t)p.sample_m + 512u : 0u;
+  const bool staged = ok && p.mode != kModeScanAll && m + fp_room <= (uint32_t)kStageKeys;
+  if (staged) {
+    for (int i = threadIdx.x; i < (int)m; i += blockDim.x) stage[i] = __ldcg(c + i);
+    __syncthreads();
+  }
+  if (ok && p.mode == kModeFused)
+    ok = merge_first_phase<DT>(p, q, ts, staged ? reinterpret_cast<unsigned long long*>(stage) : p.cand + (size_t)q * p.cap,
+                               staged ? (uint32_t)kStageKeys : (uint32_t)p.cap, &m, qs, &s_extra, &s_nredo, s_redo);
   if (!ok) {  // candidate list overflowed (adversarial row order): redo this query exactly
     const int bufcap = inline_exact_bufcap(k);
     if (bufcap <= kStageKeys) {  // right here, no extra launch
-      if (threadIdx.x == 0) ovf[q] = 0u;
       __syncthreads();
       exact_scan_body<DT>(p, q, k, bufcap, stage, qs, idx_offset, out_score, out_idx);
     } else if (threadIdx.x == 0) {
@@ -377,18 +405,24 @@ __global__ void __launch_bounds__(kSelectThreads)
     }
     return;
   }
-  if (threadIdx.x == 0) ovf[q] = 0u;
-  const unsigned long long* c = p.cand + (size_t)q * p.cap;
   int got;
-  if (cnt <= (uint32_t)kStageKeys && (int)cnt > k) {
-    for (int i = threadIdx.x; i < (int)cnt; i += blockDim.x) stage[i] = c[i];
+  if (staged) {
+    got = -1;
+    if ((int)m > k && kpad <= kFastSelectMaxK) got = block_select_bucket(stage, (int)m, k, dst, kpad, &scr.bkt);
+    if (got < 0) {
+      const uint64_t* st = stage;
+      auto key_at = [=](int i) -> unsigned long long { return st[i]; };
+      got = block_select_topk(key_at, (int)m, k, dst, kpad, &scr.sel);
+    }
+  } else if (m <= (uint32_t)kStageKeys && (int)m > k) {
+    for (int i = threadIdx.x; i < (int)m; i += blockDim.x) stage[i] = c[i];
     __syncthreads();
     const uint64_t* st = stage;
     auto key_at = [=](int i) -> unsigned long long { return st[i]; };
-    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+    got = block_select_topk(key_at, (int)m, k, dst, kpad, &scr.sel);
   } else {
     auto key_at = [=](int i) -> unsigned long long { return c[i]; };
-    got = block_select_topk(key_at, (int)cnt, k, dst, kpad, &sc);
+    got = block_select_topk(key_at, (int)m, k, dst, kpad, &scr.sel);
   }
   if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, dst, got, k, idx_offset);
   else write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
@@ -404,15 +438,16 @@ int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long
     set_error("sim_topk(select): k=%d d=%d needs %zu B of shared memory", k, p.d, smem);
     return RIR_E_ARG;
   }
+  const dim3 grid((unsigned)nq_total), block((unsigned)select_threads());
   if (dtype == RIR_BF16) {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_BF16><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_BF16>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   } else if (dtype == RIR_FP8E4M3) {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_FP8E4M3><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_FP8E4M3>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   } else {
     RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    final_select_kernel<RIR_F32><<<nq_total, select_threads(), smem, st>>>(p, k, kpad, idx_offset, out_score, out_idx, ovf);
+    RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_F32>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   }
   RIR_LAUNCH_OK();
   return RIR_OK;
@@ -512,32 +547,60 @@ __global__ void __launch_bounds__(kExactThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
-// cross-shard merge: [G, nq, k] sorted lists -> global top-k
+// cross-shard merge: [G, nq, k] lists -> global top-k
 // ---------------------------------------------------------------------------------------------
+constexpr int kMergeRankMax = 1024;  // G*k up to which the lists are ranked by counting in shared memory
+
+// Any order inside the lists (the re-ranking hook feeds unsorted scores): rank by counting, ties (only possible
+// between padding-free duplicates a caller passes in) broken by position so the result is always a permutation.
 __global__ void __launch_bounds__(kSelectThreads)
     merge_topk_kernel(const float* sc, const int32_t* ix, int G, int nq, int k, int kpad, float* out_sc,
                       int32_t* out_ix) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
+  uint64_t* all = dst + kpad;                              // [G*k] when G*k <= kMergeRankMax
   __shared__ SelectScratch scr;
   const int q = blockIdx.x;
+  const int m = G * k;
   auto key_at = [=](int i) -> unsigned long long {
     const int g = i / k, j = i - g * k;
     const size_t o = ((size_t)g * nq + q) * k + j;
     const int32_t id = ix[o];
     return id < 0 ? 0ull : make_key(sc[o], (uint32_t)id);
   };
-  const int got = block_select_topk(key_at, G * k, k, dst, kpad, &scr);
+  if (m <= kMergeRankMax) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) all[i] = key_at(i);
+    for (int i = threadIdx.x; i < kpad; i += blockDim.x) dst[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint64_t key = all[i];
+      if (key == 0ull) continue;
+      int r = 0;
+      for (int j = 0; j < m; ++j) {
+        const uint64_t o = all[j];
+        r += (o > key || (o == key && j < i)) ? 1 : 0;
+      }
+      if (r < k) dst[r] = key;
+    }
+    __syncthreads();
+    write_sorted(dst, k, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+    return;
+  }
+  const int got = block_select_topk(key_at, m, k, dst, kpad, &scr);
   write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
 }
 
-// Sharded search, receiving side: wait until every rank has published query q for this epoch, then merge G sorted
-// lists of k keys out of this rank's own inbox.
+// Sharded search, receiving side: wait until every rank has published query q for this epoch, then merge the G
+// SORTED lists of k keys out of this rank's own inbox: rank = position in the own list + number of greater keys in
+// every other list (binary searches in shared memory) — no sort.  PDL: scheduled while the select kernel drains.
 __global__ void __launch_bounds__(kSelectThreads)
     merge_exchange_kernel(const Exchange ex, int k, int kpad, float* out_sc, int32_t* out_ix) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw);  // [kpad]
+  uint64_t* lists = dst + kpad;                            // [G*k] when G*k <= kMergeStage
   __shared__ SelectScratch scr;
+  pdl_wait();
+  pdl_launch_dependents();
   const int q = blockIdx.x;
   const int b = (int)(ex.epoch & 1u);
   unsigned long long* mine = ex.inbox[ex.rank];
@@ -563,15 +626,25 @@ __global__ void __launch_bounds__(kSelectThreads)
     const int g = i / k, j = i - g * k;
     return __ldcg(base + ((size_t)g * nq_max + q) * k_max + j);
   };
-  const int got = block_select_topk(key_at, ex.G * k, k, dst, kpad, &scr);
+  const int m = ex.G * k;
+  if (m <= kMergeStage) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) lists[i] = key_at(i);
+    __syncthreads();
+    block_merge_sorted_lists(lists, ex.G, k, dst);
+    write_sorted(dst, k, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
+    return;
+  }
+  const int got = block_select_topk(key_at, m, k, dst, kpad, &scr);
   write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
 }
 
 int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st) {
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
-  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  const int m = ex.G * k;
+  const size_t smem = (size_t)(kpad + (m <= kMergeStage ? m : 0)) * sizeof(uint64_t);
   RIR_CUDA_OK(cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_exchange_kernel<<<nq, select_threads(), smem, st>>>(ex, k, kpad, out_score, out_idx);
+  RIR_CUDA_OK(launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3((unsigned)select_threads()), smem, st, ex, k, kpad,
+                         out_score, out_idx));
   RIR_LAUNCH_OK();
   return RIR_OK;
 }
@@ -623,7 +696,7 @@ extern "C" int rir_merge_topk(const float* sc, const int32_t* ix, int G, int nq,
   RIR_REQUIRE((long long)G * k < (1ll << 30), "merge_topk: G*k too large");
   if (nq == 0) return RIR_OK;
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
-  const size_t smem = (size_t)kpad * sizeof(uint64_t);
+  const size_t smem = (size_t)(kpad + ((long long)G * k <= kMergeRankMax ? G * k : 0)) * sizeof(uint64_t);
   RIR_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<nq, kSelectThreads, smem, (cudaStream_t)stream>>>(sc, ix, G, nq, k, kpad, out_sc, out_ix);
   RIR_LAUNCH_OK();

@@ -176,7 +176,9 @@ __device__ int block_select_topk(KeyAt key_at, int m, int k, uint64_t* dst, int 
     for (int i = tid; i < m; i += nthreads) {
       const unsigned long long key = key_at(i);
       const unsigned long long top = (shift >= 64) ? 0ull : (key >> shift);
-      if (top >= prefix) {
+      // key 0 is padding ("nothing"): with fewer than k real keys among m > k inputs the radix select ends at
+      // prefix 0, which every key satisfies — padding must not race the real keys for the kpad slots
+      if (top >= prefix && key != 0ull) {
         const int slot = atomicAdd(&sc->out_count, 1);
         if (slot < kpad) dst[slot] = key;
       }
@@ -190,6 +192,156 @@ __host__ __device__ __forceinline__ int pow2_ceil_int(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path for the select that follows every scan: k <= 256 out of a few thousand candidates staged in shared memory.
+// ONE histogram pass over a range-normalised score (kBuckets linear buckets between the smallest and largest ordered
+// score) finds the bucket holding the k-th key; keys above it are in for sure, the keys of that bucket compete for the
+// remaining places; both groups are ranked by counting (no sort, ~8 block barriers instead of ~30).
+// Returns k (dst[0..k) sorted descending, dst[k..kpad) = 0), or -1 when the shape is degenerate for this scheme (all
+// scores equal, or an over-full boundary bucket) and the caller must use block_select_topk.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBuckets = 2048;
+constexpr int kBoundaryMax = 512;   // keys of the boundary bucket that can be ranked here
+constexpr int kFastSelectMaxK = 256;
+
+struct BucketScratch {
+  uint32_t hist[kBuckets];
+  uint64_t sure[kFastSelectMaxK];
+  uint64_t bnd[kBoundaryMax];
+  uint32_t warp_tot[32];
+  uint32_t lo, hi;
+  int bstar, above, cb;
+  int n_sure, n_bnd;
+};
+
+__device__ __forceinline__ int block_select_bucket(const uint64_t* keys, int m, int k, uint64_t* dst, int kpad,
+                                                   BucketScratch* bs) {
+  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  // ---- range of the ordered scores ----
+  if (tid == 0) {
+    bs->lo = 0xFFFFFFFFu;
+    bs->hi = 0u;
+    bs->n_sure = 0;
+    bs->n_bnd = 0;
+    bs->bstar = -1;
+  }
+  for (int i = tid; i < kBuckets; i += nthreads) bs->hist[i] = 0u;
+  __syncthreads();
+  {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < m; i += nthreads) {
+      const uint32_t h = (uint32_t)(keys[i] >> 32);
+      lo = min(lo, h);
+      hi = max(hi, h);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(&bs->lo, lo);
+      atomicMax(&bs->hi, hi);
+    }
+  }
+  __syncthreads();
+  const uint32_t lo = bs->lo, range = bs->hi - lo;
+  if (range == 0u) return -1;  // (uniform: every thread sees the same value)
+  int shift = 32 - __clz(range) - 11;  // (range >> shift) < 2048
+  if (shift < 0) shift = 0;
+  // ---- histogram ----
+  for (int i = tid; i < m; i += nthreads) atomicAdd(&bs->hist[((uint32_t)(keys[i] >> 32) - lo) >> shift], 1u);
+  __syncthreads();
+  // ---- bucket of the k-th key, walking from the top: thread t owns buckets [NB-1-per*t-(per-1), NB-1-per*t] ----
+  {
+    const int per = kBuckets / nthreads;  // 4 at 512 threads, 16 at 128
+    uint32_t mine = 0;
+    for (int j = 0; j < per; ++j) mine += bs->hist[kBuckets - 1 - per * tid - j];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) bs->warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += bs->warp_tot[w];
+    (void)nwarps;
+    const uint32_t excl = base + incl - mine;
+    if (excl < (uint32_t)k && excl + mine >= (uint32_t)k) {  // exactly one thread
+      uint32_t cum = excl;
+      for (int j = 0; j < per; ++j) {
+        const int b = kBuckets - 1 - per * tid - j;
+        const uint32_t h = bs->hist[b];
+        if (cum < (uint32_t)k && cum + h >= (uint32_t)k) {
+          bs->bstar = b;
+          bs->above = (int)cum;
+          bs->cb = (int)h;
+        }
+        cum += h;
+      }
+    }
+  }
+  __syncthreads();
+  const int bstar = bs->bstar, above = bs->above, cb = bs->cb;
+  if (bstar < 0 || cb > kBoundaryMax || above >= kFastSelectMaxK) return -1;
+  // ---- compaction ----
+  for (int i = tid; i < m; i += nthreads) {
+    const uint64_t key = keys[i];
+    const int b = (int)(((uint32_t)(key >> 32) - lo) >> shift);
+    if (b > bstar) bs->sure[atomicAdd(&bs->n_sure, 1)] = key;
+    else if (b == bstar) bs->bnd[atomicAdd(&bs->n_bnd, 1)] = key;
+  }
+  for (int i = k + tid; i < kpad; i += nthreads) dst[i] = 0ull;
+  __syncthreads();
+  // ---- ranks by counting (keys are distinct) ----
+  const int need = k - above;
+  for (int t = tid; t < above + cb; t += nthreads) {
+    if (t < above) {
+      const uint64_t key = bs->sure[t];
+      int r = 0;
+      for (int j = 0; j < above; ++j) r += bs->sure[j] > key ? 1 : 0;
+      dst[r] = key;
+    } else {
+      const uint64_t key = bs->bnd[t - above];
+      int r = 0;
+      for (int j = 0; j < cb; ++j) r += bs->bnd[j] > key ? 1 : 0;
+      if (r < need) dst[above + r] = key;
+    }
+  }
+  __syncthreads();
+  return k;
+}
+
+// number of keys strictly greater than `key` in a list sorted descending (0 = padding, always at the end)
+__device__ __forceinline__ int count_greater_desc(const uint64_t* list, int n, uint64_t key) {
+  int lo = 0, hi = n;  // first position whose key is <= `key`
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (list[mid] > key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Merge G lists of k keys each, every list sorted descending with 0-padding at its end, real keys distinct across
+// lists: the rank of a key is its position in its own list plus, per other list, the number of greater keys (binary
+// search) — no sort.  lists[G][k] in shared memory; writes dst[0..k) (0 = fewer than k real keys in total).
+__device__ __forceinline__ void block_merge_sorted_lists(const uint64_t* lists, int G, int k, uint64_t* dst) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * k; i += blockDim.x) {
+    const int g = i / k, j = i - g * k;
+    const uint64_t key = lists[i];
+    if (key == 0ull) continue;
+    int r = j;
+    for (int o = 0; o < G && r < k; ++o)
+      if (o != g) r += count_greater_desc(lists + (size_t)o * k, k, key);
+    if (r < k) dst[r] = key;
+  }
+  __syncthreads();
 }
 
 }  // namespace rir

@@ -34,6 +34,11 @@ def _pool(x: torch.Tensor, mode: int, p: float = 3.0, eps: float = 1e-6, alpha: 
         raise TypeError(f"feature maps must be float32 or bfloat16, got {x.dtype}")
     if not x.is_cuda:
         raise TypeError("feature maps must be CUDA tensors (no CPU path)")
+    if torch.is_grad_enabled() and x.requires_grad:
+        # the kernels record no autograd graph: in the reference's TRAINING forward (RetrievalNet.GeM.forward) the
+        # backbone would silently stop receiving gradients — refuse instead of returning a detached tensor
+        raise RuntimeError("librir pooling is an inference (forward_test) path: call it under torch.no_grad() or on "
+                           "detached feature maps; use the reference's torch pooling for training")
     x = x.contiguous()
     B, C, H, W = x.shape
     out = torch.empty((B, C), dtype=torch.float32, device=x.device)
@@ -41,6 +46,13 @@ def _pool(x: torch.Tensor, mode: int, p: float = 3.0, eps: float = 1e-6, alpha: 
         _lib.check(_lib.load().rir_pool(x.data_ptr(), dt, B, C, H * W, mode, float(p), float(eps), float(alpha),
                                         float(beta), out.data_ptr(), _lib.stream_ptr()))
     return out.view(B, C, 1, 1) if keepdim else out
+
+
+def _no_param_grad(module: nn.Module) -> None:
+    """Learnable pooling parameters (p, alpha, beta) get no gradient from these kernels: refuse in training mode."""
+    if module.training and torch.is_grad_enabled() and any(t.requires_grad for t in module.parameters()):
+        raise RuntimeError(f"{type(module).__name__} (librir) does not train its parameters: switch to .eval() / "
+                           "torch.no_grad(), or use the reference module for training")
 
 
 def gem_pool(x, p=3.0, eps=1e-6, keepdim=True):
@@ -123,6 +135,7 @@ class GeMPooling(nn.Module):
         self.eps = eps
 
     def forward(self, x):
+        _no_param_grad(self)
         return gem_pool(x, float(self.p.detach().reshape(-1)[0]), self.eps)
 
 
@@ -137,6 +150,7 @@ class G2Pooling(nn.Module):
         self.beta = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
+        _no_param_grad(self)
         return _pool(x, RIR_POOL_GEM, p=float(self.p.detach()[0]), eps=self.eps, alpha=float(self.alpha.detach()[0]),
                      beta=float(self.beta.detach()[0]))
 

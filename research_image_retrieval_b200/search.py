@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PATHS, RIR_BF16, RIR_F32, RIR_FP8E4M3
+from ._lib import PATHS, RIR_BF16, RIR_F32, RIR_FP8E4M3, RIR_WS_CLEAN
 
 _DTYPES = {"bf16": RIR_BF16, "fp8": RIR_FP8E4M3, "fp32": RIR_F32}
 _TORCH_DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
@@ -123,7 +123,7 @@ class Database:
         self.n, self.d = rows.shape
         self.d_logical = d_logical or self.d
         self.rescore_rows = rescore_rows  # bf16 copy of the shard used to re-score fp8 candidates
-        self._ws = None
+        self._ws = {}   # (kind, stream) -> initialised workspace
 
     @classmethod
     def from_descriptors(cls, v: torch.Tensor, dtype: str = "bf16", idx_offset: int = 0, normalize: bool = False,
@@ -147,18 +147,38 @@ class Database:
             raise ValueError(f"query dimension {q.shape[1]} != database dimension {self.d_logical}")
         return pack_descriptors(q.to(self.rows.device), self.dtype)
 
+    def _workspace(self, kind: str, need: int) -> torch.Tensor:
+        """Scratch for the current CUDA stream, initialised once (rir_sim_topk_workspace_init): searches then pass
+        RIR_WS_CLEAN and issue no memset launches — their select kernel leaves the header ready for the next search.
+        One workspace per (kind, stream), so searches on different streams never share scratch."""
+        key = (kind, torch.cuda.current_stream(self.rows.device).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.rows.device)
+            with torch.cuda.device(self.rows.device):
+                _lib.check(_lib.load().rir_sim_topk_workspace_init(ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+            self._ws[key] = ws
+        return ws
+
+    def _drop_workspaces(self):
+        """After a failed call the header state is unknown: re-initialise on next use."""
+        self._ws.clear()
+
     def workspace(self, nq: int, k: int) -> torch.Tensor:
         need = _lib.load().rir_sim_topk_workspace(nq, self.n, self.d, k, _DTYPES[self.dtype])
         if need == 0 and not (nq == 0):
             raise ValueError(f"unsupported search shape nq={nq} n={self.n} d={self.d} k={k}")
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.rows.device)
-        return self._ws
+        return self._workspace("sim", need)
 
     def search(self, q_rows: torch.Tensor, q_scale: Optional[torch.Tensor], k: int, path: str = "auto"):
         """Exact local top-k.  Returns (scores [nq, k] fp32, idx [nq, k] int32 GLOBAL indices) on the GPU."""
-        return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
-                        idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k))
+        try:
+            return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
+                            idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k),
+                            ws_clean=True)
+        except _lib.RirError:
+            self._drop_workspaces()
+            raise
 
     def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
         """The host-facing call: fp32 CPU queries [nq, d] (pinned for an asynchronous copy) -> top-k in host buffers.
@@ -179,14 +199,17 @@ class Database:
         need = lib.rir_search_host_workspace(nq, self.n, d, k, dt)
         if need == 0:
             raise ValueError(f"unsupported search shape nq={nq} n={self.n} d={d} k={k}")
-        if getattr(self, "_ws_host", None) is None or self._ws_host.numel() < need:
-            self._ws_host = torch.empty(need, dtype=torch.uint8, device=self.rows.device)
+        ws = self._workspace("host", need)
         ex = _exchange or (1, 0, 0, 0, 0, None)
         with torch.cuda.device(self.rows.device):
-            _lib.check(lib.rir_search_host(q_host.data_ptr(), self.rows.data_ptr(), dt,
-                                           None if self.scale is None else self.scale.data_ptr(), nq, self.n, d, k,
-                                           self.idx_offset, sc.data_ptr(), ix.data_ptr(), self._ws_host.data_ptr(),
-                                           self._ws_host.numel(), PATHS[path], _lib.stream_ptr(), *ex))
+            try:
+                _lib.check(lib.rir_search_host(q_host.data_ptr(), self.rows.data_ptr(), dt,
+                                               None if self.scale is None else self.scale.data_ptr(), nq, self.n, d, k,
+                                               self.idx_offset, sc.data_ptr(), ix.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), PATHS[path] | RIR_WS_CLEAN, _lib.stream_ptr(), *ex))
+            except _lib.RirError:
+                self._drop_workspaces()
+                raise
             torch.cuda.current_stream().synchronize()
         return sc, ix
 
@@ -213,8 +236,10 @@ class Database:
 
 
 def sim_topk(Q: torch.Tensor, X: torch.Tensor, k: int, dtype: str = "bf16", q_scale=None, x_scale=None,
-             idx_offset: int = 0, path: str = "auto", workspace: Optional[torch.Tensor] = None, out=None):
-    """Thin wrapper over rir_sim_topk (include/rir.h).  Q [nq, d], X [n, d] already in the search dtype."""
+             idx_offset: int = 0, path: str = "auto", workspace: Optional[torch.Tensor] = None, out=None,
+             ws_clean: bool = False):
+    """Thin wrapper over rir_sim_topk (include/rir.h).  Q [nq, d], X [n, d] already in the search dtype.
+    ws_clean: `workspace` was initialised with rir_sim_topk_workspace_init (RIR_WS_CLEAN, see include/rir.h)."""
     lib = _lib.load()
     if dtype not in _DTYPES:
         raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
@@ -245,7 +270,9 @@ def sim_topk(Q: torch.Tensor, X: torch.Tensor, k: int, dtype: str = "bf16", q_sc
                                     None if x_scale is None else x_scale.data_ptr(), nq, n, d, k, int(idx_offset),
                                     sc.data_ptr(), ix.data_ptr(),
                                     None if workspace is None else workspace.data_ptr(),
-                                    0 if workspace is None else workspace.numel(), PATHS[path], _lib.stream_ptr()))
+                                    0 if workspace is None else workspace.numel(),
+                                    PATHS[path] | (RIR_WS_CLEAN if ws_clean and workspace is not None else 0),
+                                    _lib.stream_ptr()))
     return sc, ix
 
 
@@ -315,6 +342,12 @@ class ShardedDatabase:
         self._opened = []        # IPC mappings to close
         self._epoch = 0
         self._nq_max = self._k_max = 0
+        # rows over all shards (k is clamped to it: a list can never hold more real entries)
+        self.n_global = int(local.n)
+        if self.world > 1:
+            t = torch.tensor([int(local.n)], dtype=torch.int64, device=local.rows.device)
+            dist.all_reduce(t, group=group)
+            self.n_global = int(t.item())
 
     # ---- NVLink peer-memory exchange -----------------------------------------------------------
     def enable_peer_exchange(self, nq_max: int, k_max: int) -> bool:
@@ -398,12 +431,16 @@ class ShardedDatabase:
         ws = loc.workspace(nq, k_local)
         self._epoch += 1
         with torch.cuda.device(loc.rows.device):
-            _lib.check(lib.rir_sim_topk_sharded(
-                q_rows.data_ptr(), loc.rows.data_ptr(), _DTYPES[loc.dtype],
-                None if q_scale is None else q_scale.data_ptr(), None if loc.scale is None else loc.scale.data_ptr(),
-                nq, loc.n, loc.d, k, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), ws.data_ptr(), ws.numel(),
-                PATHS[path], _lib.stream_ptr(), self.world, self.rank, self._epoch, self._nq_max, self._k_max,
-                self._peers))
+            try:
+                _lib.check(lib.rir_sim_topk_sharded(
+                    q_rows.data_ptr(), loc.rows.data_ptr(), _DTYPES[loc.dtype],
+                    None if q_scale is None else q_scale.data_ptr(), None if loc.scale is None else loc.scale.data_ptr(),
+                    nq, loc.n, loc.d, k, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), ws.data_ptr(), ws.numel(),
+                    PATHS[path] | RIR_WS_CLEAN, _lib.stream_ptr(), self.world, self.rank, self._epoch, self._nq_max,
+                    self._k_max, self._peers))
+            except _lib.RirError:
+                loc._drop_workspaces()
+                raise
         return sc, ix
 
     def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
@@ -418,9 +455,13 @@ class ShardedDatabase:
 
     def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto"):
         """exchange: "auto" = peer memory when enabled and the batch fits the inbox, else all-gather; "nccl" forces the
-        all-gather + merge path."""
-        if (exchange != "nccl" and self._inbox is not None and 0 < q_rows.shape[0] <= self._nq_max
-                and k <= self._k_max and q_rows.is_contiguous()):
+        all-gather + merge path.  Collective: every rank must take the same branch, so the choice depends only on
+        arguments that are identical on all ranks (nq, k, the inbox shape) — never on rank-local tensor state."""
+        k = min(int(k), self.n_global)
+        q_rows = q_rows.contiguous()
+        if q_scale is not None:
+            q_scale = q_scale.contiguous()
+        if exchange != "nccl" and self._inbox is not None and 0 < q_rows.shape[0] <= self._nq_max and k <= self._k_max:
             return self._search_peer(q_rows, q_scale, k, path)
         k_local = min(k, self.local.n)
         sc, ix = self.local.search(q_rows, q_scale, k_local, path=path)

@@ -30,6 +30,8 @@ def main():
         (9, 150, 64, 100, "fp32"),        # shards shorter than k: padded lists
         (130, 90000, 64, 20, "fp8"),
         (5000, 80000, 64, 10, "bf16"),    # more than one internal query group (4096) through the exchange
+        (70, 150000 * world, 128, 100, "bf16"),  # every shard large enough for the fused scan at any world size
+        (4, 37, 64, 100, "bf16"),         # fewer rows than k in TOTAL: k clamps to the global row count
     ]
     nq_max, k_max = 5000, 100
     first = None

@@ -49,3 +49,40 @@ def test_default_workload_is_baseline_cfg2():
         n, d, k, dtype, nq, gpus = bench.N_DB, bench.DIM, bench.TOPK, "bf16", bench.NQ, 1
     assert bench.metric_name(A) == bench.METRIC
     assert "configs[1]" in bench.workload_config(A)["workload"]
+
+
+def test_both_arms_print_the_same_config_dict():
+    """The driver compares the two arms' `config`: nothing arm-specific may live there."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class A:
+        n, d, k, dtype, nq, gpus = bench.N_DB, bench.DIM, bench.TOPK, "bf16", bench.NQ, 4
+    c = bench.workload_config(A)
+    assert set(c) == {"workload", "nq", "n_db", "dim", "k", "parallelism", "l2_note"}
+    out = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--nq", "4", "--n", "3000", "--d", "32"])
+    d = json.loads([l for l in out.splitlines() if l.startswith("{")][0])
+    assert set(d["config"]) == set(c)
+    assert "scaled" not in d["cpu_baseline"]["sample"] and "full configuration" in d["cpu_baseline"]["sample"]
+
+
+def test_tie_aware_mismatch_rules():
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    ref_sc = np.array([[0.9, 0.8, 0.8000001, 0.5]], dtype=np.float32)
+    ref_ix = np.array([[3, 7, 9, 1]])
+    ok, n, _ = bench.tie_aware_mismatch(ref_sc.copy(), ref_ix.copy(), ref_sc, ref_ix, 1e-3)
+    assert ok and n == 0
+    swapped = ref_ix.copy()
+    swapped[0, 1], swapped[0, 2] = 9, 7                    # a permutation inside a tie is fine
+    ok, n, _ = bench.tie_aware_mismatch(ref_sc.copy(), swapped, ref_sc, ref_ix, 1e-3)
+    assert ok and n == 2
+    wrong = ref_ix.copy()
+    wrong[0, 0] = 5                                        # a different row with no tie around: not fine
+    ok, _, msg = bench.tie_aware_mismatch(ref_sc.copy(), wrong, ref_sc, ref_ix, 1e-3)
+    assert not ok and "without a tie" in msg
+    off = ref_sc.copy()
+    off[0, 3] = 0.51                                       # score beyond tolerance
+    ok, _, msg = bench.tie_aware_mismatch(off, ref_ix.copy(), ref_sc, ref_ix, 1e-3)
+    assert not ok and "scores differ" in msg

@@ -21,14 +21,29 @@ def test_pooling_golden(cuda_device):
     np.testing.assert_allclose(rir.gem()(x2).cpu().numpy(), g["gem_p3_x2"], **RT)
     np.testing.assert_allclose(rir.gem(p=2.5)(x).cpu().numpy(), g["gem_p2p5"], **RT)
     np.testing.assert_allclose(rir.spoc()(x).cpu().numpy(), g["spoc"], **RT)
-    np.testing.assert_allclose(rir.GeMPooling().to(cuda_device)(x).cpu().numpy(), g["gempooling_p3"], **RT)
-    np.testing.assert_allclose(rir.GeMPooling(p=4.2).to(cuda_device)(x2).cpu().numpy(), g["gempooling_p4p2"], **RT)
-    g2 = rir.G2Pooling(p=3.0)
+    # learnable-p modules are inference paths: eval() (as the reference's evaluation does) — see the refusal test below
+    np.testing.assert_allclose(rir.GeMPooling().to(cuda_device).eval()(x).cpu().numpy(), g["gempooling_p3"], **RT)
+    np.testing.assert_allclose(rir.GeMPooling(p=4.2).to(cuda_device).eval()(x2).cpu().numpy(), g["gempooling_p4p2"], **RT)
+    g2 = rir.G2Pooling(p=3.0).eval()
     g2.alpha.data.fill_(1.25)
     g2.beta.data.fill_(-0.05)
     np.testing.assert_allclose(g2(x).cpu().numpy(), g["g2"], **RT)
+    with torch.no_grad():  # training-mode module under no_grad is fine too
+        np.testing.assert_allclose(rir.GeMPooling().to(cuda_device)(x).cpu().numpy(), g["gempooling_p3"], **RT)
     np.testing.assert_allclose(rir.MACPooling()(x).cpu().numpy().reshape(3, 24, 1), g["spp_max_l1"], **RT)
     assert tuple(rir.gem()(x).shape) == (3, 24, 1, 1)
+
+
+def test_pooling_refuses_silent_no_grad(cuda_device):
+    """The kernels record no autograd graph: plugged into a TRAINING forward they must raise, not detach silently."""
+    x = torch.rand(2, 8, 4, 4, device=cuda_device)
+    with pytest.raises(RuntimeError, match="inference"):
+        rir.gem()(x.clone().requires_grad_(True))
+    with pytest.raises(RuntimeError, match="does not train"):
+        rir.GeMPooling().to(cuda_device)(x)          # training mode, learnable p, grad enabled
+    with pytest.raises(RuntimeError, match="does not train"):
+        rir.G2Pooling().to(cuda_device)(x)
+    assert tuple(rir.gem()(x).shape) == (2, 8, 1, 1)   # plain inference input is fine
 
 
 def test_heads_golden(cuda_device):

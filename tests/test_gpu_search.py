@@ -537,3 +537,109 @@ def test_rerank_hook(cuda_device):
     assert torch.equal(ri2, torch.flip(ix, dims=[1]))
     with pytest.raises(ValueError):
         rir.rerank_topk(sc, ix, lambda q, c: torch.zeros(1, device=cuda_device))
+
+
+def test_workspace_reuse_across_shapes_stays_exact(cuda_device):
+    """One Database, one (initialised, self-cleaning) workspace, many shapes in a row — fused scan, three-launch route
+    (k > 592), a failing call, 1 query, several query groups: no memset launches in between, every answer exact."""
+    n, d = 90000, 64
+    Q, X, _ = synth.retrieval_set(300, n, d, seed=5150)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr_all, _ = db.pack_queries(Q.to(cuda_device))
+    Xf, Qf = db.rows.float().cpu(), qr_all.float().cpu()
+    seq = [(70, 100, "auto"), (300, 20, "mma"), (5, 700, "mma"), (1, 10, "auto"), (70, 100, "auto"), (3, 10, "stream"),
+           (130, 50, "auto")]
+    for i, (nq, k, path) in enumerate(seq):
+        q = qr_all[:nq].contiguous()
+        sc, ix = db.search(q, None, k, path=path)
+        _check(sc, ix, Qf[:nq], Xf, k, 1e-3)
+        if i == 2:  # a call that fails after the workspace was handed over must not poison the next one
+            with pytest.raises((ValueError, rir.RirError)):
+                db.search(q, None, 9000, path=path)
+    # several internal query groups (nq > 4096) through the same workspace, then the small batch again
+    Qb, Xb, _ = synth.retrieval_set(4500, 80000, 64, seed=77)
+    dbb = rir.Database.from_descriptors(Xb.to(cuda_device), "bf16")
+    qb, _ = dbb.pack_queries(Qb.to(cuda_device))
+    sc, ix = dbb.search(qb, None, 10)
+    a = dbb.search(qb[:64].contiguous(), None, 10)
+    assert torch.equal(ix[:64], a[1]) and torch.equal(sc[:64], a[0])
+    _check(sc[4090:4110], ix[4090:4110], qb.float().cpu()[4090:4110], dbb.rows.float().cpu(), 10, 1e-3)
+
+
+def test_plain_abi_call_on_dirty_workspace(cuda_device):
+    """rir_sim_topk WITHOUT RIR_WS_CLEAN must not depend on the workspace contents (it initialises the header itself)."""
+    nq, n, d, k = 70, 100003, 128, 100
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=31337)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, _ = db.pack_queries(Q.to(cuda_device))
+    want = db.search(qr, None, k)
+    need = rir.load().rir_sim_topk_workspace(nq, n, d, k, 1)
+    ws = torch.randint(0, 255, (need,), dtype=torch.uint8, device=cuda_device)   # garbage
+    for _ in range(2):
+        got = rir.sim_topk(qr, db.rows, k, dtype="bf16", workspace=ws)
+        assert torch.equal(got[1], want[1]) and torch.equal(got[0], want[0])
+        ws[: 1 << 16].random_(0, 255)  # dirty the header again between calls
+
+
+def test_concurrent_searches_on_two_streams(cuda_device):
+    """The fused scan spins on a grid barrier: it is a cooperative launch, so two searches in flight on two streams
+    (each needs every SM) serialise at the launch instead of dead-locking.  Results must be exact on both."""
+    nq, n, d, k = 70, 160000, 256, 100
+    Q, X, _ = synth.retrieval_set(2 * nq, n, d, seed=2024)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, _ = db.pack_queries(Q.to(cuda_device))
+    qa, qb = qr[:nq].contiguous(), qr[nq:].contiguous()
+    want_a, want_b = db.search(qa, None, k), db.search(qb, None, k)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(6):
+        with torch.cuda.stream(s1):
+            ra = db.search(qa, None, k)
+        with torch.cuda.stream(s2):
+            rb = db.search(qb, None, k)
+        outs.append((ra, rb))
+    torch.cuda.synchronize()
+    for ra, rb in outs:
+        assert torch.equal(ra[1], want_a[1]) and torch.equal(ra[0], want_a[0])
+        assert torch.equal(rb[1], want_b[1]) and torch.equal(rb[0], want_b[0])
+
+
+def test_merge_topk_with_fewer_valid_entries_than_k(cuda_device):
+    """Mostly-padding lists: fewer than k real entries among G*k > k inputs (radix select ends at prefix 0) — the real
+    ones must all come out, in order, followed by (-inf, -1)."""
+    for G, nq, k, valid in [(4, 3, 100, 7), (8, 2, 1000, 3), (2, 5, 32, 0), (3, 2, 400, 150)]:
+        gen = torch.Generator().manual_seed(G * 1000 + k)
+        sc = torch.full((G, nq, k), float("-inf"))
+        ix = torch.full((G, nq, k), -1, dtype=torch.int32)
+        for g in range(G):
+            v = torch.sort(torch.rand(nq, valid, generator=gen), dim=1, descending=True).values
+            sc[g, :, :valid] = v
+            ix[g, :, :valid] = torch.arange(valid, dtype=torch.int32)[None, :] + g * 100000
+        ms, mi = rir.merge_topk(sc.to(cuda_device), ix.to(cuda_device))
+        ws, wi = S.merge_shards([sc[g].numpy() for g in range(G)], [ix[g].numpy() for g in range(G)], k)
+        np.testing.assert_array_equal(mi.cpu().numpy(), wi)
+        tot = min(k, G * valid)
+        np.testing.assert_array_equal(ms.cpu().numpy()[:, :tot], ws[:, :tot])
+        assert bool((mi[:, tot:] == -1).all()) and bool(torch.isinf(ms[:, tot:]).all())
+
+
+def test_profile_scan_hook_counts_every_query_group(cuda_device):
+    """rir_profile_scan_begin/end: one event pair per scan launch — a 4500-query search (two internal groups) records
+    two launches per call, with plausible durations."""
+    import ctypes
+    Q, X, _ = synth.retrieval_set(4500, 80000, 64, seed=78)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, _ = db.pack_queries(Q.to(cuda_device))
+    db.search(qr, None, 10)
+    lib = rir.load()
+    lib.rir_profile_scan_begin()
+    for _ in range(3):
+        db.search(qr, None, 10)
+    buf, n = (ctypes.c_float * 16)(), ctypes.c_int(0)
+    assert lib.rir_profile_scan_end(buf, 16, ctypes.byref(n)) == 0
+    assert n.value == 6
+    ms = [buf[i] for i in range(6)]
+    assert all(0.0 < m < 50.0 for m in ms)
+    lib.rir_profile_scan_begin()       # disarmed after end: a fresh begin/end with no search records nothing
+    assert lib.rir_profile_scan_end(buf, 16, ctypes.byref(n)) == 0 and n.value == 0
