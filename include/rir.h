@@ -94,10 +94,34 @@ int rir_l2_normalize(const float* x, int64_t n_rows, int d, float eps, float* ou
 int rir_whiten(const float* x, const float* W, const float* bias, int B, int C, int d_out, int l2_after, float* out,
                void* stream);
 
+/* The descriptor head as ONE call (north star "GeM / L2-norm / whitening"): feature maps x[B,C,HW] ->
+ *   pool (rir_pool semantics) -> [L2 if l2_before] -> W v + bias -> [L2 if l2_after] -> out[B, d_out] fp32.
+ * Replaces the tail of GeM.forward_test (networks/RetrievalNet.py:337-344: l2_before = 0, l2_after = 1) and of
+ * SOLAR.forward_test (networks/RetrievalNet.py:583-590: l2_before = 1, l2_after = 1).  Internally: the pooling kernel
+ * (HBM-bound, the feature maps are read once) writes the pooled descriptors as exact bf16 pairs, a tcgen05 tensor-core
+ * contraction with fp32 accumulation in TMEM applies the whitening (three split-bf16 passes: fp32-accurate to ~1e-6
+ * relative), a finishing kernel adds bias and normalises — three launches chained with programmatic dependent launch.
+ *   W12: whitening weights prepared ONCE by rir_whiten_prepare (rir_whiten_prepared_bytes(d_out, C) bytes, 16-byte
+ *   aligned); NULL = no whitening layer (pool [+ L2] only, models/gem_pooling.py:86-92; out is [B, C], d_out ignored).
+ *   workspace: rir_gem_l2_whiten_workspace(B, C, d_out) bytes (d_out = 0 without whitening), 256-byte aligned. */
+size_t rir_whiten_prepared_bytes(int d_out, int C);
+int rir_whiten_prepare(const float* W /* [d_out, C] fp32 */, int d_out, int C, void* W12, void* stream);
+size_t rir_gem_l2_whiten_workspace(int B, int C, int d_out);
+int rir_gem_l2_whiten(const void* x, int dtype, int B, int C, int HW, int mode, float p, float eps, float alpha, float beta,
+                      const void* W12, const float* bias, int d_out, int l2_before, int l2_after, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same whitening applied to already pooled descriptors x[B,C] fp32 (networks/RetrievalNet.py:342,588;
+ * networks/spca.py:61-64) on the tensor cores; workspace as for rir_gem_l2_whiten.  rir_whiten (above) is the plain
+ * fp32 CUDA-core version that takes raw weights. */
+int rir_whiten_prepared(const float* x, const void* W12, const float* bias, int B, int C, int d_out, int l2_before,
+                        int l2_after, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* PCA-whitening LEARN, dense part: column mean and covariance of descriptors X[N,D] (fp32, row-major):
  *   mean[D] = X.mean(0);  cov[D,D] = (X - mean)^T (X - mean) / N   (exactly symmetric)
  * Replaces networks/backbone.py:47-50 of pcawhitenlearn_shrinkage; the eigen-decomposition (:51-56) is done by the
- * host (research_image_retrieval_b200/whitening.py) and its W, b feed rir_whiten (networks/spca.py:215-227). */
+ * host (research_image_retrieval_b200/whitening.py) and its W, b feed rir_whiten (networks/spca.py:215-227).
+ * The covariance runs on the tensor cores (split-bf16 tcgen05 contraction over the upper triangle, fp32 accumulate);
+ * the workspace holds the transposed bf16 copy of X (4 * D * N bytes) — 256-byte aligned. */
 size_t rir_pca_covariance_workspace(int64_t N, int D);
 int rir_pca_covariance(const float* X, int64_t N, int D, float* mean, float* cov, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -9,8 +9,9 @@ switches with an import change — see INTEGRATION.md.
 from ._lib import LIB_PATH, RirError, load  # noqa: F401
 from .evaluate import compute_ap, compute_map, compute_map_and_print, revisited_map  # noqa: F401
 from .helpfunc import extract_database, extract_vectors, extract_vectors_device, scale_mean_l2  # noqa: F401
-from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, gem, gem_pool, l2n, mac_pool, spoc,  # noqa: F401
-                      spoc_pool, ultron_gem_pooling, whiten)
+from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, clear_prepared_whitening, gem,  # noqa: F401
+                      gem_l2_whiten, gem_pool, l2n, mac_pool, prepare_whitening, spoc, spoc_pool, ultron_gem_pooling,
+                      whiten)
 from .search import (Database, ShardedDatabase, alpha_query_expansion, merge_topk, pack_descriptors, rank,  # noqa: F401
                      rerank_topk, search_with_aqe, shard_bounds, sim_topk)
 

@@ -31,6 +31,13 @@ SIGNATURES = {
                          c_void_p]),
     "rir_l2_normalize": (c_int, [c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "rir_whiten": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rir_whiten_prepared_bytes": (c_size_t, [c_int, c_int]),
+    "rir_whiten_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rir_gem_l2_whiten_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "rir_gem_l2_whiten": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rir_whiten_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
     "rir_pca_covariance_workspace": (c_size_t, [c_int64, c_int]),
     "rir_pca_covariance": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rir_scale_mean_l2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),

@@ -24,6 +24,7 @@ SOURCES = [
     "rir_api.cu",
     "descriptor_build.cu",
     "pca_whiten.cu",
+    "dense_mma.cu",
     "sim_topk_stream.cu",
     "sim_topk_mma.cu",
     "sim_topk_select.cu",

@@ -59,10 +59,16 @@ __device__ __forceinline__ void unpack16<RIR_BF16>(const uint4& v, float* f) {
 
 constexpr int kPoolThreads = 256;
 
+// Optional split epilogue (fused descriptor head, dense_mma.cu): besides the fp32 value, plane (b, c) is written as an
+// exact bf16 pair v = s1 + s2 (+ a remainder below 2^-18 |v|) at [b * ld_split + c] — the operand layout of the
+// tensor-core whitening that follows, so the pooled descriptors are never re-read and re-packed by another launch.
 template <int DT, int MODE, int PK>
 __global__ void __launch_bounds__(kPoolThreads)
     pool_kernel(const void* __restrict__ x, long long planes, int hw, float p, float eps, float alpha, float beta,
-                float* __restrict__ out) {
+                float* __restrict__ out, __nv_bfloat16* __restrict__ s1, __nv_bfloat16* __restrict__ s2, int C,
+                int ld_split) {
+  pdl_wait();  // (no-op unless launched behind another kernel with programmatic stream serialization)
+  pdl_launch_dependents();
   constexpr int ESZ = DT == RIR_F32 ? 4 : 2;
   constexpr int EPC = 16 / ESZ;
   const PoolOp<MODE, PK> op{p, eps};
@@ -106,31 +112,56 @@ __global__ void __launch_bounds__(kPoolThreads)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc = op.merge(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-    if (lane == 0) out[pl] = fmaf(alpha, op.finish(acc, hw), beta);
+    if (lane == 0) {
+      const float v = fmaf(alpha, op.finish(acc, hw), beta);
+      out[pl] = v;
+      if (s1 != nullptr) {
+        const long long b = pl / C;
+        const size_t o = (size_t)b * ld_split + (size_t)(pl - b * C);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        s1[o] = h;
+        s2[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
   }
 }
 
+struct SplitOut {
+  __nv_bfloat16 *s1, *s2;
+  int C, ld;
+};
+
 template <int DT, int MODE, int PK>
 static int launch_pool(const void* x, long long planes, int hw, float p, float eps, float alpha, float beta,
-                       float* out, cudaStream_t st) {
+                       float* out, cudaStream_t st, const SplitOut& so) {
   const long long warps_needed = planes;
   long long blocks = (warps_needed + (kPoolThreads / 32) - 1) / (kPoolThreads / 32);
   const long long max_blocks = (long long)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
   if (blocks > max_blocks) blocks = max_blocks;
-  pool_kernel<DT, MODE, PK><<<(unsigned)blocks, kPoolThreads, 0, st>>>(x, planes, hw, p, eps, alpha, beta, out);
+  pool_kernel<DT, MODE, PK><<<(unsigned)blocks, kPoolThreads, 0, st>>>(x, planes, hw, p, eps, alpha, beta, out, so.s1,
+                                                                       so.s2, so.C, so.ld);
   RIR_LAUNCH_OK();
   return RIR_OK;
 }
 
 template <int DT>
 static int dispatch_pool(const void* x, long long planes, int hw, int mode, float p, float eps, float alpha,
-                         float beta, float* out, cudaStream_t st) {
-  if (mode == RIR_POOL_MAX) return launch_pool<DT, RIR_POOL_MAX, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st);
-  if (mode == RIR_POOL_AVG) return launch_pool<DT, RIR_POOL_AVG, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st);
-  if (p == 3.0f) return launch_pool<DT, RIR_POOL_GEM, kPow3>(x, planes, hw, p, eps, alpha, beta, out, st);
-  if (p == 2.0f) return launch_pool<DT, RIR_POOL_GEM, kPow2>(x, planes, hw, p, eps, alpha, beta, out, st);
-  if (p == 1.0f) return launch_pool<DT, RIR_POOL_GEM, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st);
-  return launch_pool<DT, RIR_POOL_GEM, kPowGeneric>(x, planes, hw, p, eps, alpha, beta, out, st);
+                         float beta, float* out, cudaStream_t st, const SplitOut& so) {
+  if (mode == RIR_POOL_MAX) return launch_pool<DT, RIR_POOL_MAX, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+  if (mode == RIR_POOL_AVG) return launch_pool<DT, RIR_POOL_AVG, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+  if (p == 3.0f) return launch_pool<DT, RIR_POOL_GEM, kPow3>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+  if (p == 2.0f) return launch_pool<DT, RIR_POOL_GEM, kPow2>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+  if (p == 1.0f) return launch_pool<DT, RIR_POOL_GEM, kPow1>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+  return launch_pool<DT, RIR_POOL_GEM, kPowGeneric>(x, planes, hw, p, eps, alpha, beta, out, st, so);
+}
+
+// pooling with the optional split-bf16 epilogue (arguments validated by the callers)
+int launch_pool_split(const void* x, int dtype, int B, int C, int HW, int mode, float p, float eps, float alpha, float beta,
+                      float* pooled, __nv_bfloat16* s1, __nv_bfloat16* s2, int ld_split, cudaStream_t st) {
+  const SplitOut so{s1, s2, C, ld_split};
+  const long long planes = (long long)B * C;
+  if (dtype == RIR_F32) return dispatch_pool<RIR_F32>(x, planes, HW, mode, p, eps, alpha, beta, pooled, st, so);
+  return dispatch_pool<RIR_BF16>(x, planes, HW, mode, p, eps, alpha, beta, pooled, st, so);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +207,9 @@ static int launch_l2(const float* x, long long n, int d, float eps, float* out, 
   l2_normalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, d, eps, out);
   RIR_LAUNCH_OK();
   return RIR_OK;
+}
+int launch_l2_rows(const float* x, long long n, int d, float eps, float* out, cudaStream_t st) {
+  return launch_l2(x, n, d, eps, out, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -304,9 +338,7 @@ extern "C" int rir_pool(const void* x, int dtype, int B, int C, int HW, int mode
   RIR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "pool: feature maps must be 16-byte aligned");
   const long long planes = (long long)B * C;
   if (planes == 0) return RIR_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == RIR_F32) return dispatch_pool<RIR_F32>(x, planes, HW, mode, p, eps, alpha, beta, out, st);
-  return dispatch_pool<RIR_BF16>(x, planes, HW, mode, p, eps, alpha, beta, out, st);
+  return launch_pool_split(x, dtype, B, C, HW, mode, p, eps, alpha, beta, out, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int rir_l2_normalize(const float* x, int64_t n_rows, int d, float eps, float* out, void* stream) {

@@ -8,11 +8,15 @@
 // model; research_image_retrieval_b200/whitening.py), its output feeds rir_whiten.
 //
 //   col_sum_kernel / col_mean_kernel : two-stage column mean, deterministic (no atomics)
-//   cov_syrk_kernel                  : C = (X - m)^T (X - m) / N, fp32 FMA (the reference's precision), 128x128 tile per
-//                                      CTA, 8x8 micro-tile per thread, 16-row K steps staged in shared memory; only
-//                                      tiles with bj >= bi are computed and mirrored, so C is exactly symmetric
+//   covariance                       : C = (X - m)^T (X - m) / N on the tensor cores — the centred descriptors are
+//                                      transposed and split into exact bf16 pairs once, then dense_mma.cu's
+//                                      split-bf16 tcgen05 contraction (fp32 accumulate in TMEM) runs over the upper
+//                                      triangle of tiles and a finishing kernel mirrors it, so C is exactly symmetric
 //                                      (== the reference's (Xcov + Xcov.T) / 2).
-// Work: 2*N*D^2 / 2 flops; N = 20,000 descriptors x D = 2048: 84 GFLOP, ~3 ms.  Bytes: N*D*4 per column-block pass.
+//   cov_syrk_kernel                  : the round-1 fp32-FMA CUDA-core SYRK, kept as an independent implementation for
+//                                      the parity tests and timings (RIR_PCA_FP32=1).
+// Work: 2*N*D^2 / 2 flops (x3 bf16 passes); N = 20,000 descriptors x D = 2048: 84 GFLOP fp32-equivalent.
+#include <stdlib.h>
 #include "rir_common.cuh"
 
 namespace rir {
@@ -127,13 +131,23 @@ __global__ void __launch_bounds__(kCovThreads)
   }
 }
 
+// dense_mma.cu
+size_t syrk_split_workspace(long long N, int D);
+int syrk_split_bf16(const float* X, const float* mean, long long N, int D, float* cov, void* workspace, cudaStream_t st);
+
+static bool pca_use_fp32() {
+  static const int v = getenv("RIR_PCA_FP32") ? atoi(getenv("RIR_PCA_FP32")) : 0;
+  return v != 0;
+}
+static size_t col_partial_bytes(int D) { return ((size_t)kRowSplits * (size_t)D * sizeof(float) + 255) / 256 * 256; }
+
 }  // namespace rir
 
 using namespace rir;
 
 extern "C" size_t rir_pca_covariance_workspace(int64_t N, int D) {
-  (void)N;
-  return D > 0 ? (size_t)kRowSplits * (size_t)D * sizeof(float) : 0;
+  if (D < 1 || N < 1) return 0;
+  return col_partial_bytes(D) + syrk_split_workspace(N, D);
 }
 
 extern "C" int rir_pca_covariance(const float* X, int64_t N, int D, float* mean, float* cov, void* workspace,
@@ -141,6 +155,7 @@ extern "C" int rir_pca_covariance(const float* X, int64_t N, int D, float* mean,
   if (int e = check_arch()) return e;
   RIR_REQUIRE(N >= 1 && D >= 1, "pca_covariance: bad shape N=%lld D=%d", (long long)N, D);
   RIR_REQUIRE(X && mean && cov && workspace, "pca_covariance: null pointer");
+  RIR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pca_covariance: workspace must be 256-byte aligned");
   RIR_REQUIRE(workspace_bytes >= rir_pca_covariance_workspace(N, D), "pca_covariance: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
@@ -149,8 +164,11 @@ extern "C" int rir_pca_covariance(const float* X, int64_t N, int D, float* mean,
   RIR_LAUNCH_OK();
   col_mean_kernel<<<(D + kColThreads - 1) / kColThreads, kColThreads, 0, st>>>(partial, N, D, mean);
   RIR_LAUNCH_OK();
-  const int T = (D + kCovTile - 1) / kCovTile;
-  cov_syrk_kernel<<<T * (T + 1) / 2, kCovThreads, 0, st>>>(X, mean, N, D, cov);
-  RIR_LAUNCH_OK();
-  return RIR_OK;
+  if (pca_use_fp32()) {
+    const int T = (D + kCovTile - 1) / kCovTile;
+    cov_syrk_kernel<<<T * (T + 1) / 2, kCovThreads, 0, st>>>(X, mean, N, D, cov);
+    RIR_LAUNCH_OK();
+    return RIR_OK;
+  }
+  return syrk_split_bf16(X, mean, N, D, cov, reinterpret_cast<uint8_t*>(workspace) + col_partial_bytes(D), st);
 }

@@ -2,7 +2,7 @@
 `ConvDimReduction` (networks/spca.py:205-227).
 
 The dense part (column mean, centred covariance of the N x D descriptors) runs in `rir_pca_covariance`
-(csrc/pca_whiten.cu); the D x D symmetric eigen-decomposition is an offline, once-per-model step and uses
+(csrc/pca_whiten.cu: the covariance is a split-bf16 tcgen05 contraction, csrc/dense_mma.cu); the D x D symmetric eigen-decomposition is an offline, once-per-model step and uses
 `torch.linalg.eigh` in fp64 on the GPU (the reference calls `np.linalg.eig` on the same symmetric matrix).
 Eigenvectors are defined up to sign, exactly as in the reference; cosine similarities of whitened descriptors do not
 depend on it.
@@ -43,7 +43,7 @@ def pcawhitenlearn_shrinkage(X, s: float = 1.0, device=None):
     mean, cov = pca_covariance(Xt)
     w, V = torch.linalg.eigh(cov.double())           # ascending
     w, V = torch.flip(w, dims=[0]), torch.flip(V, dims=[1])
-    P = torch.diag(w.pow(-0.5 * s)) @ V.t()
+    P = w.pow(-0.5 * s)[:, None] * V.t()             # diag(w^-s/2) V^T as a row scaling (no D x D GEMM)
     out_dtype = X.dtype if isinstance(X, np.ndarray) else np.float32
     return mean.reshape(1, -1).cpu().numpy().astype(out_dtype), P.t().contiguous().cpu().numpy().astype(out_dtype)
 

@@ -112,6 +112,59 @@ def test_whiten(cuda_device, B, C, dout):
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5)
     got = rir.whiten(x.to(cuda_device).view(B, C, 1, 1), W.to(cuda_device).view(dout, C, 1, 1), None, l2_after=True)
     np.testing.assert_allclose(got.cpu().numpy(), D.l2n(D.whiten(x, W, None)).numpy(), rtol=1e-4, atol=2e-6)
+    # the plain fp32 CUDA-core kernel (rir_whiten) stays available and agrees
+    got = rir.whiten(x.to(cuda_device), W.to(cuda_device), b.to(cuda_device), exact_fp32=True).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,C,hw,dout,dtype", [(64, 2048, 8, 2048, torch.float32), (130, 2048, 4, 512, torch.float32),
+                                               (9, 100, 5, 70, torch.float32), (33, 1024, 7, 300, torch.bfloat16),
+                                               (256, 512, 4, 2048, torch.float32)])
+@pytest.mark.parametrize("l2_before", [False, True])
+def test_fused_head_tensor_core(cuda_device, B, C, hw, dout, dtype, l2_before):
+    """rir_gem_l2_whiten (pool -> split-bf16 tcgen05 whitening -> bias + L2) vs the fp32 torch oracle: the split keeps
+    fp32 accuracy (rtol 1e-4 like the reference-golden head tests; measured error ~1e-6)."""
+    fm = synth.feature_maps(B, C, hw, hw, seed=B + C)
+    if dtype == torch.bfloat16:
+        fm = fm.to(torch.bfloat16).float()
+    gen = torch.Generator().manual_seed(dout)
+    W = torch.randn(dout, C, generator=gen) / C ** 0.5
+    b = torch.randn(dout, generator=gen) / 10
+    layer = torch.nn.Linear(C, dout)
+    layer.weight.data, layer.bias.data = W, b
+    head = rir.DescriptorHead("gem", whiten_layer=layer.to(cuda_device), l2_before_whiten=l2_before)
+    got = head(fm.to(cuda_device).to(dtype)).cpu().numpy()
+    want = D.head(fm, "gem", W=W, b=b, l2_before_whiten=l2_before).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6)
+    assert abs(float(np.linalg.norm(got[0])) - 1.0) < 1e-5
+    # second call re-uses the prepared weights; an in-place weight update (one that autograd's version counter sees:
+    # optimizer steps, load_state_dict, no_grad in-place ops) must be picked up
+    with torch.no_grad():
+        layer.weight.mul_(-1.0)
+    got2 = head(fm.to(cuda_device).to(dtype)).cpu().numpy()
+    want2 = D.head(fm, "gem", W=-W, b=b, l2_before_whiten=l2_before).numpy()
+    np.testing.assert_allclose(got2, want2, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_head_without_whitening(cuda_device):
+    fm = synth.feature_maps(5, 96, 6, 6, seed=12)
+    got = rir.DescriptorHead("gem")(fm.to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(got, D.head(fm, "gem").numpy(), rtol=1e-5, atol=1e-7)
+    got = rir.DescriptorHead("mac")(fm.to(cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(got, D.head(fm, "mac").numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_pca_covariance_tensor_core_sizes(cuda_device):
+    """Split-bf16 tcgen05 covariance vs fp64 numpy, shapes that are not tile multiples; exactly symmetric."""
+    for N, Dm in [(3001, 300), (1000, 2048), (70, 40)]:
+        X = torch.randn(N, Dm, generator=torch.Generator().manual_seed(N + Dm)).numpy()
+        X = (X / np.linalg.norm(X, axis=1, keepdims=True)).astype(np.float32) + 0.01
+        mean, cov = rir.pca_covariance(torch.from_numpy(X).to(cuda_device))
+        Xd = X.astype(np.float64)
+        cref = (Xd - Xd.mean(0)).T @ (Xd - Xd.mean(0)) / N
+        scale = np.abs(cref).max()
+        assert np.abs(cov.cpu().numpy() - cref).max() <= 2e-4 * scale
+        assert torch.equal(cov, cov.t())
 
 
 def test_scale_mean_l2(cuda_device):
