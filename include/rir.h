@@ -259,6 +259,37 @@ int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t ld, const i
                     const int32_t* proto, int P, const int32_t* kappas, int nk, double* map, double* aps, double* mpr,
                     double* prs, int32_t* status, void* stream);
 
+/* The same evaluation for a COMPACT list: row q holds only the query's ground-truth ids, ordered by their position
+ * in the full ranking, and positions[nq, ld] gives that position (0-based, ascending along the row; ignored where
+ * ranks is -1).  Everything else as rir_compute_map.  Used with rir_rank_count below when the full ranked list is
+ * never materialised (R1M: 1M distractors per query). */
+int rir_compute_map_at(const int32_t* ranks, const int32_t* positions, int nq, int64_t L, int64_t ld, const int32_t* a_ids,
+                       const int32_t* a_off, const int32_t* b_ids, const int32_t* b_off, const int32_t* c_ids,
+                       const int32_t* c_off, const int32_t* proto, int P, const int32_t* kappas, int nk, double* map,
+                       double* aps, double* mpr, double* prs, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Positions of ground-truth ids in the full ranking WITHOUT sorting the database: what
+ * `np.arange(N)[np.in1d(ranks[:, i], ok)]` (utils/evaluate.py:76-80) reads off the reference's full
+ * np.argsort (iris_evaluate.py:386).  position(p) = #{rows x : (score(x), -index(x)) > (score(p), -index(p))} —
+ * a count, so it shards: each rank counts over its rows, one all-reduce adds the counts.
+ *   ids / off: CSR of the GLOBAL row ids to locate per query (off[nq+1], total_ids = off[nq]).
+ *   1. rir_gnd_scores: scores[i] = <q, x_id> for ids whose row lives in this shard, 0 otherwise (all-reduce SUM over
+ *      the shards gives every rank every score);
+ *   2. rir_rank_thresholds: keys_sorted[nq, m_pad] (uint64 ranking keys: ordered score << 32 | ~id), each row sorted
+ *      descending and 0-padded; m_pad = power of two in [32, 4096] >= the longest id list;
+ *   3. rir_rank_count: counts[nq, m_pad] = shard rows that outrank threshold j of query q (all-reduce SUM over the
+ *      shards gives the position); workspace >= nq * m_pad * 4 bytes.  Queries and rows as in rir_sim_topk.
+ * ------------------------------------------------------------------------------------------ */
+int rir_gnd_scores(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                   int64_t n_local, int d, int64_t idx_offset, const int32_t* ids, const int32_t* off, int64_t total_ids,
+                   float* scores, void* stream);
+int rir_rank_thresholds(const float* scores, const int32_t* ids, const int32_t* off, int nq, int m_pad,
+                        uint64_t* keys_sorted, void* stream);
+int rir_rank_count(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
+                   int64_t n_local, int d, int64_t idx_offset, const uint64_t* keys_sorted, int m_pad, int32_t* counts,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

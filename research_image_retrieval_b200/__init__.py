@@ -7,7 +7,8 @@ The module names mirror the reference's (`src/benchmark/utils/{evaluate,helpfunc
 switches with an import change — see INTEGRATION.md.
 """
 from ._lib import LIB_PATH, RirError, load  # noqa: F401
-from .evaluate import compute_ap, compute_map, compute_map_and_print, revisited_map  # noqa: F401
+from .evaluate import (compute_ap, compute_map, compute_map_and_print, compute_map_full, gnd_positions,  # noqa: F401
+                       revisited_map, revisited_map_full)
 from .helpfunc import extract_database, extract_vectors, extract_vectors_device, scale_mean_l2  # noqa: F401
 from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, clear_prepared_whitening, gem,  # noqa: F401
                       gem_l2_whiten, gem_pool, l2n, mac_pool, prepare_whitening, spoc, spoc_pool, ultron_gem_pooling,

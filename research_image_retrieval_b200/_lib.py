@@ -74,6 +74,14 @@ SIGNATURES = {
     "rir_compute_map": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rir_compute_map_at": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, POINTER(c_int32), c_int, POINTER(c_int32), c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rir_gnd_scores": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p,
+                               c_void_p, c_int64, c_void_p, c_void_p]),
+    "rir_rank_thresholds": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rir_rank_count": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p,
+                               c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -30,6 +30,7 @@ SOURCES = [
     "sim_topk_select.cu",
     "query_expansion.cu",
     "evaluate_map.cu",
+    "rank_positions.cu",
 ]
 
 NVCC_FLAGS = [

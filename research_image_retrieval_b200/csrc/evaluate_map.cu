@@ -20,6 +20,8 @@ constexpr int kMaxKappa = 16;
 
 struct MapParams {
   const int32_t* ranks;
+  const int32_t* positions;  // optional [nq, ld]: position of list entry j in the FULL ranking (ascending along j);
+                             // nullptr: the entry's own index j (the list IS the ranking, possibly truncated)
   int nq;
   long long L, ld;
   const int32_t* ids[3];
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(kMapThreads) map_per_query_kernel(const MapPar
       const int ex_junk = block_excl_count(isjunk, warp_tot, &tot_junk);
       if (isok) {
         const long long i = (long long)s_npos[pr] + ex_ok;           // ordinal of this positive
-        const long long r = j - ((long long)s_njunk[pr] + ex_junk);  // junk-adjusted 0-based rank
+        const long long pj = p.positions ? (long long)p.positions[(size_t)q * p.ld + j] : j;
+        const long long r = pj - ((long long)s_njunk[pr] + ex_junk);  // junk-adjusted 0-based rank
         const double p0 = (r == 0) ? 1.0 : __ddiv_rn((double)i, (double)r);
         const double p1 = __ddiv_rn((double)(i + 1), (double)(r + 1));
         term[ex_ok] = __ddiv_rn(__dmul_rn(__dadd_rn(p0, p1), rstep[pr]), 2.0);
@@ -201,10 +204,10 @@ __global__ void map_reduce_kernel(const MapParams p) {
 
 using namespace rir;
 
-extern "C" int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t ld, const int32_t* a_ids,
-                               const int32_t* a_off, const int32_t* b_ids, const int32_t* b_off, const int32_t* c_ids,
-                               const int32_t* c_off, const int32_t* proto, int P, const int32_t* kappas, int nk,
-                               double* map, double* aps, double* mpr, double* prs, int32_t* status, void* stream) {
+static int compute_map_impl(const int32_t* ranks, const int32_t* positions, int nq, int64_t L, int64_t ld,
+                            const int32_t* a_ids, const int32_t* a_off, const int32_t* b_ids, const int32_t* b_off,
+                            const int32_t* c_ids, const int32_t* c_off, const int32_t* proto, int P, const int32_t* kappas,
+                            int nk, double* map, double* aps, double* mpr, double* prs, int32_t* status, void* stream) {
   if (int e = check_arch()) return e;
   RIR_REQUIRE(nq >= 1 && L >= 0 && ld >= L, "compute_map: bad shape nq=%d L=%lld ld=%lld", nq, (long long)L, (long long)ld);
   RIR_REQUIRE(ranks || L == 0, "compute_map: null ranks");
@@ -212,7 +215,7 @@ extern "C" int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t 
   RIR_REQUIRE(nk >= 0 && nk <= kMaxKappa && (nk == 0 || kappas), "compute_map: 0..%d kappas", kMaxKappa);
   RIR_REQUIRE(map && aps && status && (nk == 0 || (mpr && prs)), "compute_map: null output");
   MapParams p;
-  p.ranks = ranks; p.nq = nq; p.L = L; p.ld = ld;
+  p.ranks = ranks; p.positions = positions; p.nq = nq; p.L = L; p.ld = ld;
   p.ids[0] = a_ids; p.off[0] = a_off; p.ids[1] = b_ids; p.off[1] = b_off; p.ids[2] = c_ids; p.off[2] = c_off;
   // proto / kappas are HOST arrays (tiny): they travel in the kernel parameter block
   for (int i = 0; i < kMaxProto; ++i) p.proto[i] = i < P ? proto[i] : 0;
@@ -226,4 +229,22 @@ extern "C" int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t 
   map_reduce_kernel<<<1, 32, 0, st>>>(p);
   RIR_LAUNCH_OK();
   return RIR_OK;
+}
+
+extern "C" int rir_compute_map(const int32_t* ranks, int nq, int64_t L, int64_t ld, const int32_t* a_ids,
+                               const int32_t* a_off, const int32_t* b_ids, const int32_t* b_off, const int32_t* c_ids,
+                               const int32_t* c_off, const int32_t* proto, int P, const int32_t* kappas, int nk,
+                               double* map, double* aps, double* mpr, double* prs, int32_t* status, void* stream) {
+  return compute_map_impl(ranks, nullptr, nq, L, ld, a_ids, a_off, b_ids, b_off, c_ids, c_off, proto, P, kappas, nk, map,
+                          aps, mpr, prs, status, stream);
+}
+
+extern "C" int rir_compute_map_at(const int32_t* ranks, const int32_t* positions, int nq, int64_t L, int64_t ld,
+                                  const int32_t* a_ids, const int32_t* a_off, const int32_t* b_ids, const int32_t* b_off,
+                                  const int32_t* c_ids, const int32_t* c_off, const int32_t* proto, int P,
+                                  const int32_t* kappas, int nk, double* map, double* aps, double* mpr, double* prs,
+                                  int32_t* status, void* stream) {
+  RIR_REQUIRE(positions != nullptr || L == 0, "compute_map_at: null positions");
+  return compute_map_impl(ranks, positions, nq, L, ld, a_ids, a_off, b_ids, b_off, c_ids, c_off, proto, P, kappas, nk, map,
+                          aps, mpr, prs, status, stream);
 }

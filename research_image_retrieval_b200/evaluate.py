@@ -74,7 +74,7 @@ def _dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
 
 
-def _run_map(rows, L, nq, lists_abc, protos, keeps, device=None):
+def _run_map(rows, L, nq, lists_abc, protos, keeps, device=None, positions=None):
     """Launch rir_compute_map; returns host numpy (map[P], aps[P,nq], mpr[P,nk], prs[P,nq,nk], status[P,nq]).
 
     Two host->device copies (ranked lists; all id lists + offsets packed into one int32 array) and ONE device->host
@@ -111,9 +111,18 @@ def _run_map(rows, L, nq, lists_abc, protos, keeps, device=None):
     proto_arr = (ctypes.c_int32 * P)(*protos)
     kappa_arr = (ctypes.c_int32 * nk1)(*([int(k) for k in keeps] or [0]))
     with torch.cuda.device(device):
-        _lib.check(lib.rir_compute_map(rows_d.data_ptr(), nq, int(L), int(ld), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
-                                       ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk, base + 8 * o_map, base + 8 * o_aps,
-                                       base + 8 * o_mpr, base + 8 * o_prs, base + 8 * n_f64, _lib.stream_ptr()))
+        if positions is None:
+            _lib.check(lib.rir_compute_map(rows_d.data_ptr(), nq, int(L), int(ld), ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                           ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk, base + 8 * o_map,
+                                           base + 8 * o_aps, base + 8 * o_mpr, base + 8 * o_prs, base + 8 * n_f64,
+                                           _lib.stream_ptr()))
+        else:  # compact lists of ground-truth ids + their positions in the full ranking (rir_rank_count)
+            pos_d = _dev(positions, device)
+            assert tuple(pos_d.shape) == tuple(rows_d.shape) and pos_d.dtype == torch.int32 and pos_d.is_contiguous()
+            _lib.check(lib.rir_compute_map_at(rows_d.data_ptr(), pos_d.data_ptr(), nq, int(L), int(ld), ptrs[0], ptrs[1],
+                                              ptrs[2], ptrs[3], ptrs[4], ptrs[5], proto_arr, P, kappa_arr, nk,
+                                              base + 8 * o_map, base + 8 * o_aps, base + 8 * o_mpr, base + 8 * o_prs,
+                                              base + 8 * n_f64, _lib.stream_ptr()))
     host = out.cpu().numpy()
     f64 = host[: n_f64 * 8].view(np.float64)
     status = host[n_f64 * 8:].view(np.int32).reshape(P, nq)
@@ -187,6 +196,93 @@ def revisited_map(ranks, gnd, kappas=(1, 5, 10), li=False):
     kappas = list(kappas)
     m, aps, mpr, prs, status = _run_map(rows, L, nq, [easy, hard, junk], [PROTO_EASY, PROTO_MEDIUM, PROTO_HARD], kappas)
     return [_finish(m[p], aps[p], mpr[p], prs[p], status[p], kappas) for p in range(3)]
+
+
+# ----------------------------------------------------------------------------------------------
+# full-protocol evaluation without a full ranking (R1M: +1M distractors)
+# ----------------------------------------------------------------------------------------------
+def gnd_positions(db, q_rows, q_scale, id_lists):
+    """Positions of the given database ids in each query's FULL ranking (score descending, ties -> lower index) over a
+    Database or ShardedDatabase — what `np.arange(N)[np.in1d(ranks[:, i], ids)]` reads off the reference's complete
+    np.argsort (utils/evaluate.py:76-80, iris_evaluate.py:386), computed as counts: position(p) = number of rows
+    that outrank p.  Each shard counts over its own rows; two small all-reduces (scores, counts) join the shards.
+
+    id_lists: per query an array of GLOBAL row ids.  Returns (ranked_ids [nq, m_pad] int32 CUDA — the query's ids in
+    rank order, -1 padded —, positions [nq, m_pad] int32 CUDA)."""
+    import torch.distributed as dist
+
+    from .search import _DTYPES, ShardedDatabase
+    local = db.local if isinstance(db, ShardedDatabase) else db
+    sharded = isinstance(db, ShardedDatabase) and db.world > 1
+    nq = q_rows.shape[0]
+    if len(id_lists) != nq:
+        raise ValueError("one id list per query")
+    uniq = [np.unique(np.asarray(l).reshape(-1).astype(np.int64)) for l in id_lists]
+    ids, off = ids_to_csr(uniq)
+    longest = max((u.size for u in uniq), default=0)
+    m_pad = 32
+    while m_pad < longest:
+        m_pad *= 2
+    if m_pad > 4096:
+        raise ValueError(f"at most 4096 ground-truth ids per query (got {longest})")
+    dev = local.rows.device
+    lib = _lib.load()
+    dt = _DTYPES[local.dtype]
+    ids_d = _dev(ids if ids.size else np.zeros(1, dtype=np.int32), dev)
+    off_d = _dev(off, dev)
+    scores = torch.zeros(max(int(off[-1]), 1), dtype=torch.float32, device=dev)
+    qs_ptr = None if q_scale is None else q_scale.data_ptr()
+    xs_ptr = None if local.scale is None else local.scale.data_ptr()
+    q_rows = q_rows.contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rir_gnd_scores(q_rows.data_ptr(), local.rows.data_ptr(), dt, qs_ptr, xs_ptr, nq, local.n, local.d,
+                                      local.idx_offset, ids_d.data_ptr(), off_d.data_ptr(), int(off[-1]),
+                                      scores.data_ptr(), _lib.stream_ptr()))
+    if sharded:
+        dist.all_reduce(scores, group=db.group)       # every id is scored by exactly one shard
+    keys = torch.empty((nq, m_pad), dtype=torch.int64, device=dev)   # uint64 ranking keys
+    counts = torch.empty((nq, m_pad), dtype=torch.int32, device=dev)
+    ws = torch.empty(nq * m_pad * 4, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rir_rank_thresholds(scores.data_ptr(), ids_d.data_ptr(), off_d.data_ptr(), nq, m_pad,
+                                           keys.data_ptr(), _lib.stream_ptr()))
+        _lib.check(lib.rir_rank_count(q_rows.data_ptr(), local.rows.data_ptr(), dt, qs_ptr, xs_ptr, nq, local.n, local.d,
+                                      local.idx_offset, keys.data_ptr(), m_pad, counts.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _lib.stream_ptr()))
+    if sharded:
+        dist.all_reduce(counts, group=db.group)
+    ranked = (0xFFFFFFFF - (keys & 0xFFFFFFFF)).to(torch.int32)
+    ranked = torch.where(keys == 0, torch.full_like(ranked, -1), ranked)
+    return ranked.contiguous(), counts
+
+
+def revisited_map_full(db, q_rows, q_scale, gnd, kappas=(1, 5, 10)):
+    """Easy / Medium / Hard over the FULL ranking of a (sharded) database that is never sorted or materialised:
+    [(mAP, aps, mpr, prs)] * 3, equal to revisited_map(full_ranks, gnd, kappas) on the complete ranked lists."""
+    nq = len(gnd)
+    lists = [np.concatenate([np.asarray(g["easy"]).reshape(-1), np.asarray(g["hard"]).reshape(-1),
+                             np.asarray(g["junk"]).reshape(-1)]) for g in gnd]
+    ranked, pos = gnd_positions(db, q_rows, q_scale, lists)
+    easy = ids_to_csr([g["easy"] for g in gnd])
+    hard = ids_to_csr([g["hard"] for g in gnd])
+    junk = ids_to_csr([g["junk"] for g in gnd])
+    kappas = list(kappas)
+    m, aps, mpr, prs, status = _run_map(ranked, ranked.shape[1], nq, [easy, hard, junk],
+                                        [PROTO_EASY, PROTO_MEDIUM, PROTO_HARD], kappas, positions=pos)
+    return [_finish(m[p], aps[p], mpr[p], prs[p], status[p], kappas) for p in range(3)]
+
+
+def compute_map_full(db, q_rows, q_scale, gnd, keeps=None):
+    """compute_map (utils/evaluate.py:37-150) over the full ranking of a (sharded) database, via gnd_positions."""
+    nq = len(gnd)
+    junk_lists = [g["junk"] if "junk" in g else [] for g in gnd]
+    lists = [np.concatenate([np.asarray(g["ok"]).reshape(-1), np.asarray(j).reshape(-1)]) for g, j in zip(gnd, junk_lists)]
+    ranked, pos = gnd_positions(db, q_rows, q_scale, lists)
+    ok = ids_to_csr([g["ok"] for g in gnd])
+    junk = ids_to_csr(junk_lists)
+    m, aps, mpr, prs, status = _run_map(ranked, ranked.shape[1], nq, [ok, None, junk], [PROTO_OK_A_JUNK_C], keeps,
+                                        positions=pos)
+    return _finish(m[0], aps[0], mpr[0], prs[0], status[0], keeps)
 
 
 def compute_map_and_print(dataset, featuretype, mode, ranks, gnd, kappas=[1, 5, 10], verbose=False, li=False):

@@ -74,6 +74,21 @@ def main():
             assert ok, f"case {ci}: {msg}"
         sdb.close()
         first = first or True
+    # full-protocol mAP by counting: every shard counts the rows that outrank each ground-truth id, two
+    # all-reduces join them — must equal the unsharded evaluation bit for bit (same per-row arithmetic, integer counts)
+    nq, n, d = 12, 60000, 64
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=555)
+    gnd = synth.revisited_gnd(nq, n, seed=556, n_empty_easy=1)
+    lo, hi = rir.shard_bounds(n, world, rank)
+    db = rir.Database.from_descriptors(X[lo:hi].to(dev), "bf16", idx_offset=lo)
+    sdb = rir.ShardedDatabase(db)
+    qr, qs = db.pack_queries(Q.to(dev))
+    got = rir.revisited_map_full(sdb, qr, qs, gnd)
+    whole = rir.Database.from_descriptors(X.to(dev), "bf16")
+    want = rir.revisited_map_full(whole, qr, qs, gnd)
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
     dist.barrier()
     if rank == 0:
         print("multi-gpu worker OK")
