@@ -151,12 +151,38 @@ def golden_ranking(ref):
     return {"ranking": dict(q=q.numpy(), g=g.numpy(), sim=sim, ranks=ranks, topk_scores=sc.numpy(), topk_idx=ix.numpy())}
 
 
+def golden_iris_copy(ref):
+    """The duplicate copy of compute_map_and_print inside the entry script (iris_evaluate.py:189-265) run on the inputs
+    of map_full.npz: its report spells "Easy", unknown names print + return (None, None, None), and the old-protocol
+    branch raises ValueError like the utils copy."""
+    iris = ref_adapter.load_iris_copy()
+    with np.load(os.path.join(OUT, "map_full.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    nq = len(g["easy_off"]) - 1
+    gnd = [{k: g[f"{k}_ids"][g[f"{k}_off"][i]:g[f"{k}_off"][i + 1]] for k in ("easy", "hard", "junk")} for i in range(nq)]
+    (vals, text) = ref_adapter.quiet(iris.compute_map_and_print, "roxford5k", "golden", "global", g["ranks"], gnd, [1, 5, 10], True)
+    (unk, unk_text) = ref_adapter.quiet(iris.compute_map_and_print, "holidays", "golden", "global", g["ranks"], gnd)
+    assert unk == (None, None, None)
+    try:
+        ref_adapter.quiet(iris.compute_map_and_print, "oxford5k", "golden", "global", g["ranks"],
+                          [{"ok": x["easy"], "junk": x["junk"]} for x in gnd])
+        old = "no exception"
+    except Exception as e:  # noqa: BLE001
+        old = type(e).__name__
+    return {"iris_copy": dict(mapE=vals[0], mapM=vals[1], mapH=vals[2], text=text, unknown_text=unk_text, old_protocol=old)}
+
+
 def main():
     ref = ref_adapter.load()
     os.makedirs(OUT, exist_ok=True)
     allc = {}
-    for fn in (golden_map, golden_pooling, golden_extract, golden_ranking):
+    only = set(sys.argv[1:])  # e.g. `python oracle/make_golden.py iris_copy` regenerates one fixture
+    for fn in (golden_map, golden_pooling, golden_extract, golden_ranking, golden_iris_copy):
+        if only and fn.__name__.replace("golden_", "") not in only and not (fn is golden_map and only & {"map_full", "map_truncated", "map_kat"}):
+            continue
         allc.update(fn(ref))
+    if only:
+        allc = {k: v for k, v in allc.items() if k in only}
     for name, arrays in allc.items():
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})

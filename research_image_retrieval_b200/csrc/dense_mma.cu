@@ -170,7 +170,7 @@ struct DensePlan {
 // diagonal of a covariance over 20,000 rows: 3 x 313 chunks x 4 MMAs) drifts by ~1e-4 relative (measured).  K is
 // therefore split so that no accumulation chain exceeds kMaxChainChunks chunks; the partial tiles are added by the
 // finishing kernels in IEEE fp32, in a fixed order.
-constexpr int kMaxChainChunks = 48;
+constexpr int kMaxChainChunks = 64;
 
 static DensePlan dense_plan(long long M, long long N, long long K, bool upper_only) {
   DensePlan pl;
@@ -305,16 +305,56 @@ __global__ void __launch_bounds__(256)
   }
   float ss = 0.f;
   float* o = out + (size_t)b * d_out;
-  for (int j = threadIdx.x; j < d_out; j += 256) {
-    float v = 0.f;
-    for (int s = 0; s < S; ++s) v += __ldcg(partial + ((size_t)s * mp + b) * np + j);  // fixed order
-    v = fmaf(v, inv_in, bias ? bias[j] : 0.f);
-    o[j] = v;
-    ss = fmaf(v, v, ss);
+  // 128-bit loads, four splits in flight per thread (the per-element chain over S is latency-bound otherwise: this
+  // kernel took 26 us for 256 x 2048 outputs with scalar loads, more than the contraction itself).  The sum over the
+  // splits keeps its fixed order s = 0, 1, 2, ...
+  const float* prow = partial + (size_t)b * np;
+  const size_t sstride = (size_t)mp * np;
+  const bool vec = (d_out & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 &&
+                   (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < d_out; j += 256 * 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int s = 0;
+      for (; s + 4 <= S; s += 4) {
+        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)(s + 0) * sstride + j));
+        const float4 a1 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)(s + 1) * sstride + j));
+        const float4 a2 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)(s + 2) * sstride + j));
+        const float4 a3 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)(s + 3) * sstride + j));
+        acc.x = ((acc.x + a0.x) + a1.x) + a2.x + a3.x; acc.y = ((acc.y + a0.y) + a1.y) + a2.y + a3.y;
+        acc.z = ((acc.z + a0.z) + a1.z) + a2.z + a3.z; acc.w = ((acc.w + a0.w) + a1.w) + a2.w + a3.w;
+      }
+      for (; s < S; ++s) {
+        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)s * sstride + j));
+        acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+      }
+      const float4 bb = bias ? *reinterpret_cast<const float4*>(bias + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v;
+      v.x = fmaf(acc.x, inv_in, bb.x); v.y = fmaf(acc.y, inv_in, bb.y);
+      v.z = fmaf(acc.z, inv_in, bb.z); v.w = fmaf(acc.w, inv_in, bb.w);
+      *reinterpret_cast<float4*>(o + j) = v;
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+  } else {
+    for (int j = threadIdx.x; j < d_out; j += 256) {
+      float v = 0.f;
+      for (int s = 0; s < S; ++s) v += __ldcg(prow + (size_t)s * sstride + j);  // fixed order
+      v = fmaf(v, inv_in, bias ? bias[j] : 0.f);
+      o[j] = v;
+      ss = fmaf(v, v, ss);
+    }
   }
   if (l2_after) {
     const float denom = fmaxf(sqrtf(block_sum(ss)), 1e-12f);
-    for (int j = threadIdx.x; j < d_out; j += 256) o[j] = o[j] / denom;  // own elements
+    if (vec) {
+      for (int j = threadIdx.x * 4; j < d_out; j += 256 * 4) {  // own elements
+        float4 v = *reinterpret_cast<float4*>(o + j);
+        v.x /= denom; v.y /= denom; v.z /= denom; v.w /= denom;
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    } else {
+      for (int j = threadIdx.x; j < d_out; j += 256) o[j] = o[j] / denom;  // own elements
+    }
   }
 }
 

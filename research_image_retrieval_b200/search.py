@@ -111,6 +111,21 @@ def pack_descriptors(v: torch.Tensor, dtype: str = "bf16"):
     return out, scale
 
 
+class PendingQuery:
+    """Handle of an enqueued host-buffer search (Database.query_host_async)."""
+
+    def __init__(self, event, sc, ix, q_host):
+        self._event, self._sc, self._ix = event, sc, ix
+        self._q_host = q_host   # keeps the (pinned) query buffer alive until the copy has run
+
+    def done(self) -> bool:
+        return self._event.query()
+
+    def result(self):
+        self._event.synchronize()
+        return self._sc, self._ix
+
+
 class Database:
     """One resident shard of database descriptors in the layout the search kernels read.
 
@@ -180,12 +195,12 @@ class Database:
             self._drop_workspaces()
             raise
 
-    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
-        """The host-facing call: fp32 CPU queries [nq, d] (pinned for an asynchronous copy) -> top-k in host buffers.
-
-        One C-ABI call (rir_search_host) enqueues H2D -> pack -> search -> D2H on the current stream; this method
-        synchronises the stream and returns (scores [nq, k] fp32, idx [nq, k] int32) CPU tensors (`out` to re-use
-        pinned result buffers)."""
+    def query_host_async(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
+        """Enqueue the host-facing call and return at once: fp32 CPU queries [nq, d] (pinned for an asynchronous copy)
+        -> top-k written into host buffers.  One C-ABI call (rir_search_host) enqueues H2D -> pack -> search -> D2H on
+        the current stream.  Returns a PendingQuery; `.result()` waits for THIS call only and returns
+        (scores [nq, k] fp32, idx [nq, k] int32) CPU tensors.  A serving loop keeps two batches in flight (distinct
+        `out` buffers) so the device never idles between them."""
         if q_host.is_cuda or q_host.dtype != torch.float32 or q_host.dim() != 2 or not q_host.is_contiguous():
             raise TypeError("query_host expects a contiguous float32 CPU tensor [nq, d]")
         nq, d = q_host.shape
@@ -210,8 +225,13 @@ class Database:
             except _lib.RirError:
                 self._drop_workspaces()
                 raise
-            torch.cuda.current_stream().synchronize()
-        return sc, ix
+            done = torch.cuda.Event()
+            done.record()
+        return PendingQuery(done, sc, ix, q_host)
+
+    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
+        """query_host_async(...).result(): the synchronous host-facing call (`out` to re-use pinned result buffers)."""
+        return self.query_host_async(q_host, k, out=out, path=path, _exchange=_exchange).result()
 
     def query(self, q: torch.Tensor, k: int, path: str = "auto"):
         """fp32 queries [nq, d_logical] -> top-k.  With a rescoring copy: fp8 scan for 2k+16 candidates, then a bf16
@@ -443,15 +463,21 @@ class ShardedDatabase:
                 raise
         return sc, ix
 
-    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
-        """Database.query_host over the sharded database (peer exchange must be enabled for world > 1)."""
+    def query_host_async(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
+        """Database.query_host_async over the sharded database (peer exchange must be enabled for world > 1).  Calls
+        are collective and must be issued in the same order on every rank; at most two may be in flight (the inbox
+        has two parities)."""
         if self.world == 1:
-            return self.local.query_host(q_host, k, out=out, path=path)
+            return self.local.query_host_async(q_host, k, out=out, path=path)
         if self._inbox is None or q_host.shape[0] > self._nq_max or k > self._k_max:
             raise ValueError("enable_peer_exchange(nq_max, k_max) first (and keep nq, k within it)")
         self._epoch += 1
-        return self.local.query_host(q_host, k, out=out, path=path,
-                                     _exchange=(self.world, self.rank, self._epoch, self._nq_max, self._k_max, self._peers))
+        return self.local.query_host_async(q_host, k, out=out, path=path,
+                                           _exchange=(self.world, self.rank, self._epoch, self._nq_max, self._k_max,
+                                                      self._peers))
+
+    def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
+        return self.query_host_async(q_host, k, out=out, path=path).result()
 
     def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto"):
         """exchange: "auto" = peer memory when enabled and the batch fits the inbox, else all-gather; "nccl" forces the

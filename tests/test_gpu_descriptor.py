@@ -135,7 +135,8 @@ def test_fused_head_tensor_core(cuda_device, B, C, hw, dout, dtype, l2_before):
     head = rir.DescriptorHead("gem", whiten_layer=layer.to(cuda_device), l2_before_whiten=l2_before)
     got = head(fm.to(cuda_device).to(dtype)).cpu().numpy()
     want = D.head(fm, "gem", W=W, b=b, l2_before_whiten=l2_before).numpy()
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6)
+    # unit-norm rows: absolute error stays below 3e-6 of the norm (measured ~1e-6) — near-zero components need the atol
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=3e-6)
     assert abs(float(np.linalg.norm(got[0])) - 1.0) < 1e-5
     # second call re-uses the prepared weights; an in-place weight update (one that autograd's version counter sees:
     # optimizer steps, load_state_dict, no_grad in-place ops) must be picked up
@@ -143,7 +144,7 @@ def test_fused_head_tensor_core(cuda_device, B, C, hw, dout, dtype, l2_before):
         layer.weight.mul_(-1.0)
     got2 = head(fm.to(cuda_device).to(dtype)).cpu().numpy()
     want2 = D.head(fm, "gem", W=-W, b=b, l2_before_whiten=l2_before).numpy()
-    np.testing.assert_allclose(got2, want2, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got2, want2, rtol=1e-4, atol=3e-6)
 
 
 def test_fused_head_without_whitening(cuda_device):

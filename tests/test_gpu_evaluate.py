@@ -249,3 +249,32 @@ def test_full_ranking_map_sharded_emulation(cuda_device):
         total += c
     torch.cuda.synchronize()
     assert torch.equal(total, pos)
+
+
+def test_iris_evaluate_copy_conventions(cuda_device):
+    """The duplicate copy inside the entry script (iris_evaluate.py:189-265): same numbers, "Easy" spelling, unknown
+    dataset -> message + (None, None, None), old protocol -> ValueError.  Text compared byte for byte with the
+    reference's own output (tests/golden/iris_copy.npz, generated by oracle/make_golden.py from the unmodified file)."""
+    from research_image_retrieval_b200 import iris_evaluate as IE
+    g, gi = load_golden("map_full"), load_golden("iris_copy")
+    gnd = _gnd(g, ["easy", "hard", "junk"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        out = IE.compute_map_and_print("roxford5k", "golden", "global", g["ranks"], gnd, [1, 5, 10], True)
+    assert buf.getvalue() == str(gi["text"])
+    assert tuple(float(x) for x in out) == (float(gi["mapE"]), float(gi["mapM"]), float(gi["mapH"]))
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        out = IE.compute_map_and_print("holidays", "golden", "global", g["ranks"], gnd)
+    assert out == (None, None, None) and buf.getvalue() == str(gi["unknown_text"])
+    assert str(gi["old_protocol"]) == "ValueError"
+    with pytest.raises(ValueError):
+        IE.compute_map_and_print("oxford5k", "golden", "global", g["ranks"], [{"ok": x["easy"], "junk": x["junk"]} for x in gnd])
+    # the script's evaluation tail (:378-398) end to end: normalise -> rank -> report
+    r = load_golden("ranking")
+    gnd6 = synth.revisited_gnd(6, 300, seed=11, n_empty_easy=0)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        got = IE.evaluate_features(torch.from_numpy(r["q"]), torch.from_numpy(r["g"]), gnd6, "rparis6k", verbose=False)
+    want = E.compute_map_and_print_values(r["ranks"].T, gnd6)
+    assert tuple(float(x) for x in got) == tuple(float(x) for x in want)

@@ -61,3 +61,18 @@ def test_pca_whitening_learn(ref):
     np.testing.assert_allclose(np.abs(P), np.abs(np.real(P_ref)), rtol=1e-6, atol=1e-9)  # eigenvector sign is free
     Y = (X - m) @ P
     np.testing.assert_allclose(np.cov(Y.T, bias=True), np.eye(20), atol=1e-8)
+
+
+def test_iris_copy_matches_utils_copy_and_golden():
+    """a13': the duplicate evaluation functions inside iris_evaluate.py (cut out of the unmodified file) give the same
+    numbers as utils/evaluate.py on the golden inputs; the committed iris_copy fixture is what they print."""
+    from conftest import csr_to_lists, load_golden
+    iris = ref_adapter.load_iris_copy()
+    g, gi = load_golden("map_full"), load_golden("iris_copy")
+    nq = len(g["easy_off"]) - 1
+    lists = {k: csr_to_lists(g[f"{k}_ids"], g[f"{k}_off"]) for k in ("easy", "hard", "junk")}
+    gnd = [{k: lists[k][i] for k in lists} for i in range(nq)]
+    (vals, text) = ref_adapter.quiet(iris.compute_map_and_print, "roxford5k", "golden", "global", g["ranks"], gnd, [1, 5, 10], True)
+    assert text == str(gi["text"]) and "mAP Easy" in text
+    assert tuple(float(v) for v in vals) == (float(g["mapE"]), float(g["mapM"]), float(g["mapH"]))
+    assert iris.compute_ap(np.array([1, 3]), 2) == 1 / 3 and iris.compute_ap(np.array([0, 1, 2]), 3) == 1.0   # SURVEY §8c KATs
