@@ -248,6 +248,7 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
   if (ex) {
     exl = *ex;
     exl.k_push = k_req;
+    exl.fold = 0;
     ex = &exl;
   }
 
@@ -273,6 +274,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     return RIR_E_WORKSPACE;
   }
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  // one query group whose select CTAs are all co-resident: the select kernel merges the peers' lists itself
+  if (ex && nq <= pl.group && select_can_fold_merge(nq, ex->G, k_req)) exl.fold = 1;
 
   for (int g0 = 0; g0 < nq; g0 += pl.group) {
     const int gq = (nq - g0) < pl.group ? (nq - g0) : pl.group;
@@ -392,7 +395,7 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     }
   }
   // sharded: every rank's lists are on their way into the inboxes; wait for all G of them and merge
-  if (ex) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
+  if (ex && !ex->fold) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
   return RIR_OK;
 }
 

@@ -38,6 +38,7 @@ struct Exchange {
   int nq_max, k_max;
   int q_base;       // global query index of this launch's query 0
   int k_push;       // list length every rank publishes (the global k; a shard shorter than k pads with 0 keys)
+  int fold;         // 1: the select kernel also waits for the peers' lists and merges (no separate merge launch)
   unsigned long long* inbox[kMaxPeers];  // inbox of rank g as mapped in THIS process
 };
 __host__ __device__ __forceinline__ size_t exchange_key_slots(int G, int nq_max, int k_max) {
@@ -90,6 +91,8 @@ struct SimParams {
   long long perm_mul;    // physical tile = (virtual tile * perm_mul) % perm_n
   long long perm_n;      // number of database tiles
   int tile_rows;         // rows per database tile of the fused scan (256 or 128)
+  int range_rows;        // range mode (sim_topk_mma.cu): first-phase slot s covers rows [s * range_rows, + first_rows);
+  int first_rows;        //   0 = classic mode (slot s is tile (s * perm_mul) % perm_n)
   int k;                 // top-k requested (the fused scan computes tau itself)
   Exchange ex;           // sharded search: push the local top-k to the peers instead of writing out_score / out_idx
   // development: per-CTA event timeline of the tcgen05 scan (rir_profile_timeline); null in production
@@ -125,6 +128,7 @@ int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
 bool select_handles_overflow(int k);  // the select kernel redoes overflowed queries itself (no fallback launch needed)
+bool select_can_fold_merge(int nq_total, int G, int k_push);
 int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st);
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                       int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);

@@ -95,7 +95,20 @@ struct MmaGeom {
   int tile_n;         // database rows per tile: 256, or 128 when a small shard would leave the last round mostly idle
   int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue (timing
                       // decomposition of mainloop vs epilogue; results are garbage)
+  // Range mode (fused scan of one query block): CTA b owns the CONTIGUOUS rows [b * range_rows, (b + 1) * range_rows)
+  // and walks them as tiles of h_first, 256, ..., 256, h_last rows — every CTA streams the same number of bytes, so
+  // the last round is as full as the others (148 CTAs x 3.32 tiles used to run as 4 rounds with the last one 32 %
+  // occupied and HBM under-subscribed).  The ragged tile (h < 256) goes through its own tensor map (box = h rows) and
+  // an N = h tcgen05.mma.  0 = classic mode (tiles dealt round-robin).
+  int range_rows, h_first, h_last;
 };
+
+// range mode: rows and height of CTA b's tile in round rd
+__device__ __forceinline__ void range_tile(const MmaGeom& g, int b, long long rd, long long* row0, int* h) {
+  const long long off = rd == 0 ? 0 : (long long)g.h_first + (rd - 1) * 256;
+  *row0 = (long long)b * g.range_rows + off;
+  *h = rd == 0 ? g.h_first : (rd == g.rounds - 1 ? g.h_last : 256);
+}
 
 enum { kShareNone = 0, kShareQ = 1, kShareX = 2 };
 
@@ -252,7 +265,7 @@ __device__ __forceinline__ float pick16(const float (&v)[16], int j) {
 template <int DT, int MB, int TWO>
 __global__ void __launch_bounds__(128 + 128 * MB, 1)
     sim_mma_kernel(const SimParams p, const MmaGeom g, const __grid_constant__ CUtensorMap tmQ,
-                   const __grid_constant__ CUtensorMap tmX) {
+                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kNumBuf = 2 / MB;             // TMEM accumulator buffers
   constexpr int kBufCols = kTileN * MB;       // columns per buffer
@@ -304,6 +317,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   if ((warp == 0 || warp == 3) && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmXr);
   }
   if (warp == 2) {
     if (TWO) {
@@ -347,7 +361,21 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         long long v;
         int sb;
         item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
-        const int row0 = (int)tile_row0(v);
+        int row0 = (int)tile_row0(v);
+        if (!TWO && g.range_rows > 0) {  // range mode: my own contiguous rows, ragged tile through its own map
+          long long r0;
+          int h;
+          range_tile(g, (int)blockIdx.x, rd, &r0, &h);
+          for (int kc = 0; kc < g.kchunks; ++kc) {
+            mbar_wait(&tail->empty_b[s], ph ^ 1u);
+            if (kc == 0) tl_mark(p, 1, rd);
+            mbar_expect_tx(&tail->full_b[s], (uint32_t)(h * 128));
+            tma_tensor2d_g2s(ring_b + (size_t)s * kBSlot, h == kTileN ? &tmX : &tmXr, kc * kElemsPerChunk, (int)r0,
+                             &tail->full_b[s], pol_x);
+            if (++s == g.nb) { s = 0; ph ^= 1u; }
+          }
+          continue;
+        }
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->empty_b[s], ph ^ 1u);
           if (kc == 0) tl_mark(p, 1, rd);
@@ -421,6 +449,13 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         tc_fence_after();
         tl_mark(p, 2, rd);
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kBufCols);
+        uint32_t idesc = g.idesc;
+        if (!TWO && g.range_rows > 0) {  // ragged tile: N = its height
+          long long r0;
+          int h;
+          range_tile(g, (int)blockIdx.x, rd, &r0, &h);
+          idesc = (g.idesc & ~(0x3Fu << 17)) | ((uint32_t)(h >> 3) << 17);
+        }
         for (int kc = 0; kc < g.kchunks; ++kc) {
           mbar_wait(&tail->full_a[sa], pha);
           mbar_wait(&tail->full_b[sb_], phb);
@@ -436,11 +471,11 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
               const uint32_t dcol = d_tmem + (uint32_t)(m * kTileN);
               const uint32_t acc = (uint32_t)((kc | j) != 0);
               if (TWO) {
-                if (DT == RIR_BF16) umma_f16_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
-                else umma_f8_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+                if (DT == RIR_BF16) umma_f16_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, idesc, acc);
+                else umma_f8_2sm(dcol, a_desc + 2u * j, b_desc + 2u * j, idesc, acc);
               } else {
-                if (DT == RIR_BF16) umma_f16(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
-                else umma_f8(dcol, a_desc + 2u * j, b_desc + 2u * j, g.idesc, acc);
+                if (DT == RIR_BF16) umma_f16(dcol, a_desc + 2u * j, b_desc + 2u * j, idesc, acc);
+                else umma_f8(dcol, a_desc + 2u * j, b_desc + 2u * j, idesc, acc);
               }
             }
           }
@@ -534,9 +569,16 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       long long v;
       int sb;
       item_of(g, rd, cluster_id, nclusters, crank, &v, &sb);
-      const long long row0 = tile_row0(v);
+      long long row0 = tile_row0(v);
+      int tile_h = g.tile_n;                      // rows (= accumulator columns) of this round's tile
+      bool tile_real = v < g.ntiles;
+      if (!TWO && g.range_rows > 0) {
+        range_tile(g, (int)blockIdx.x, rd, &row0, &tile_h);
+        tile_real = row0 < p.n;
+        v = blockIdx.x;                           // first-phase slot of this CTA in sample_keys
+      }
       const int q = (sb * MB + mblk) * kTileM + ew * 32 + lane;
-      const bool qvalid = q < p.nq && v < g.ntiles;
+      const bool qvalid = q < p.nq && tile_real;
       if (q != pend_q) {
         if (npend > 0) reserve();
         pend_q = q;
@@ -571,7 +613,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       const int xb = (int)(rd & 1);
       const __nv_bfloat162 ts2 = __float2bfloat162_rn(ts);
       if (p.x_scale) {  // stage this tile's row scales (uniform branch)
-        for (int j = etid; j < g.tile_n; j += kEpiThreads) {
+        for (int j = etid; j < tile_h; j += kEpiThreads) {
           const long long row = row0 + j;
           tail->xs[xb][j] = row < p.n ? p.x_scale[row] : 0.f;
         }
@@ -705,27 +747,27 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         uint32_t va[16], vb[16];
         // (uniform) first-phase pre-pass — pays off once many lanes collect at the same time (divergence); with a
         // handful of queries the second TMEM pass costs more than it saves (1 query, 126 k-row shard: +4 us)
-        if (mode == kModeSample && p.topt == kMaxTopT && g.tile_n >= 16 * kMaxTopT && p.nq >= 16) {
+        if (mode == kModeSample && p.topt == kMaxTopT && tile_h >= 16 * kMaxTopT && p.nq >= 16) {
           tmem_ld_32x32_x16(taddr, va);
 #pragma unroll 1
-          for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
+          for (int c0 = 0; c0 < tile_h; c0 += 32) {
             tmem_ld_wait();
             tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 16), vb);
             prepass16(va, c0);
             tmem_ld_wait();
-            if (c0 + 32 < g.tile_n) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
+            if (c0 + 32 < tile_h) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
             prepass16(vb, c0 + 16);
           }
           thr0 = t8[kMaxTopT - 1];
         }
         tmem_ld_32x32_x16(taddr, va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < g.tile_n; c0 += 32) {
+        for (int c0 = 0; c0 < tile_h; c0 += 32) {
           tmem_ld_wait();
           tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 16), vb);
           process16(va, c0);
           tmem_ld_wait();
-          if (c0 + 32 < g.tile_n) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
+          if (c0 + 32 < tile_h) tmem_ld_32x32_x16(taddr + (uint32_t)(c0 + 32), va);
           process16(vb, c0 + 16);
         }
       }
@@ -737,7 +779,10 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         else mbar_arrive(&tail->tmem_empty[ab]);
       }
       if (++ab == kNumBuf) { ab = 0; aph ^= 1u; }
-      if (mode == kModeSample && p.topt > 0 && qvalid) {  // slot = (query, sample tile): every slot is written
+      // slot = (query, sample tile): EVERY slot is written.  Range mode: the last CTA(s) may own no real row at all —
+      // their slots must read "nothing" (top[] is still all zero), not whatever an earlier search left there (a stale
+      // key above the true k-th score would raise tau and drop real neighbours).
+      if (mode == kModeSample && p.topt > 0 && (qvalid || (g.range_rows > 0 && q < p.nq))) {
 #pragma unroll
         for (int i = 0; i < kMaxTopT; ++i)
           if (i < p.topt) p.sample_keys[(size_t)q * p.sample_m + (size_t)v * p.topt + i] = top[i];
@@ -858,7 +903,7 @@ bool mma_fused_disabled() { return g_fused_launch_mode == 1; }
 
 template <int DT, int MB, int TWO>
 static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
-                        unsigned grid, cudaStream_t st) {
+                        const CUtensorMap& tmXr, unsigned grid, cudaStream_t st) {
   const size_t smem_bytes =
       (size_t)g.nb * (TWO ? kBBytes / 2 : kBBytes) + (size_t)g.na * kABytes * MB + sizeof(MmaSmemTail);
   cudaLaunchConfig_t cfg = {};
@@ -888,7 +933,7 @@ static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap&
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB, TWO>, p, g, tmQ, tmX);
+    return cudaLaunchKernelEx(&cfg, sim_mma_kernel<DT, MB, TWO>, p, g, tmQ, tmX, tmXr);
   };
   if (!g.fused) {
     RIR_CUDA_OK(launch_with(false, true));
@@ -942,9 +987,10 @@ static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap&
 
 template <int DT>
 static int launch_mma_d(const SimParams& p, const MmaGeom& g, const CUtensorMap& tmQ, const CUtensorMap& tmX,
-                        unsigned grid, int mb, int two, cudaStream_t st) {
-  if (two) return mb == 1 ? launch_mma_t<DT, 1, 1>(p, g, tmQ, tmX, grid, st) : launch_mma_t<DT, 2, 1>(p, g, tmQ, tmX, grid, st);
-  return mb == 1 ? launch_mma_t<DT, 1, 0>(p, g, tmQ, tmX, grid, st) : launch_mma_t<DT, 2, 0>(p, g, tmQ, tmX, grid, st);
+                        const CUtensorMap& tmXr, unsigned grid, int mb, int two, cudaStream_t st) {
+  if (two)
+    return mb == 1 ? launch_mma_t<DT, 1, 1>(p, g, tmQ, tmX, tmXr, grid, st) : launch_mma_t<DT, 2, 1>(p, g, tmQ, tmX, tmXr, grid, st);
+  return mb == 1 ? launch_mma_t<DT, 1, 0>(p, g, tmQ, tmX, tmXr, grid, st) : launch_mma_t<DT, 2, 0>(p, g, tmQ, tmX, tmXr, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1120,11 +1166,49 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     if (env_int("RIR_MMA_PERM", 1) == 0) mul = 1;  // tuning override (development only)
     p.perm_mul = mul;
   }
-  CUtensorMap tmQ, tmX;
+  // Range mode (see MmaGeom): one query block, no CTA pairs — every CTA streams its own contiguous rows.
+  g.range_rows = g.h_first = g.h_last = 0;
+  p.range_rows = p.first_rows = 0;
+  int ragged = 0;  // height of the one tile per CTA that is not 256 rows (0: none)
+  if (g.fused && g.nsb == 1 && !two && g.tile_n == kTileN && env_int("RIR_MMA_RANGE", 1) != 0) {
+    long long R = (p.n + grid - 1) / grid;
+    R = (R + 31) / 32 * 32;
+    int t = (int)(R % kTileN);
+    if (t == 0) t = kTileN;
+    if (t < 64) {  // a 32-row tile is not worth a round: lengthen the ranges by 32 rows (the last CTA takes the slack)
+      R += 64 - t;
+      t = 64;
+    }
+    const int full = (int)((R - t) / kTileN);  // >= 1: the fused scan needs >= 2 tiles per CTA
+    // Which tile is the sample?  The ragged one first means a smaller sample but thresholds that are known before the
+    // first full tile has streamed in (no stall of the accumulator ring); it must still keep the candidate lists
+    // short: expected survivors per query ~ k * R / h_first.
+    // Measured (70 queries, 125,916-row shard): ragged tile first 98.3 us — its first-phase epilogue cannot use the
+    // unit-maxima pre-pass (fewer than 8 units) and takes as long as a full tile's — ragged tile LAST 95.7 us (the
+    // un-overlapped final epilogue covers 96 columns instead of 256), classic round-robin 98.3 us.  Default: last.
+    int tail_first = 0;
+    {
+      const int o = env_int("RIR_MMA_SAMPLE_TAIL", -1);  // tuning override (development only)
+      if (o == 1 && t >= 64 && (long long)p.k * R / t <= 4000) tail_first = 1;
+    }
+    if (full >= 1 && R * (long long)grid < (1ll << 31)) {
+      g.range_rows = (int)R;
+      g.h_first = tail_first ? t : kTileN;
+      g.h_last = tail_first ? kTileN : t;
+      g.rounds = full + 1;
+      ragged = t == kTileN ? 0 : t;
+      p.range_rows = (int)R;
+      p.first_rows = g.h_first;
+    }
+  }
+  CUtensorMap tmQ, tmX, tmXr;
   if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, two ? g.a_rows / g.npairs : g.a_rows / ca)) return e;
   if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, g.tile_n / cb)) return e;
-  if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, grid, mb, two, st);
-  return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, grid, mb, two, st);
+  tmXr = tmX;
+  if (ragged > 0)
+    if (int e = make_rowmajor_map(&tmXr, p.X, p.n, p.d, dtype, ragged)) return e;
+  if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, tmXr, grid, mb, two, st);
+  return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, tmXr, grid, mb, two, st);
 }
 
 }  // namespace rir

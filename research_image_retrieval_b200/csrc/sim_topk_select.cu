@@ -119,6 +119,45 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
   }
 }
 
+// Sharded search with the merge FOLDED into the select kernel (ex.fold: every query's CTA is co-resident, i.e. at most
+// one CTA per SM): push this rank's list, wait until all G ranks have published query q for this epoch, merge the G
+// sorted lists out of this rank's own inbox and write the global top-k — no separate merge launch.  Nobody waits
+// before having pushed, and every waiting CTA is resident, so the wait cannot dead-lock.  `lists` holds >= G * k_push
+// keys, `mdst` >= k_push keys (shared memory).  All threads of the block must call.
+__device__ __forceinline__ void exchange_and_merge(const Exchange& ex, int q, const uint64_t* sorted, int got, int k,
+                                                   long long idx_offset, uint64_t* lists, uint64_t* mdst, float* out_score,
+                                                   int32_t* out_idx) {
+  push_sorted_to_peers(ex, q, sorted, got, k, idx_offset);
+  if (!ex.fold) return;
+  const int b = (int)(ex.epoch & 1u);
+  const int qg = ex.q_base + q;
+  unsigned long long* mine = ex.inbox[ex.rank];
+  if ((int)threadIdx.x < ex.G) {
+    const uint32_t* f = exchange_flag(mine, ex, b, threadIdx.x, qg);
+    const long long t0 = clock64();
+    while (true) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == ex.epoch) break;
+      __nanosleep(100);
+      if (clock64() - t0 > 20000000000ll) {
+        printf("librir: rank %d never received query %d of rank %d (epoch %u, saw %u)\n", ex.rank, qg, (int)threadIdx.x,
+               ex.epoch, v);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int kp = ex.k_push;
+  for (int i = threadIdx.x; i < ex.G * kp; i += blockDim.x) {
+    const int g = i / kp, j = i - g * kp;
+    lists[i] = __ldcg(exchange_keys(mine, ex, b, g, qg) + j);
+  }
+  __syncthreads();
+  block_merge_sorted_lists(lists, ex.G, kp, mdst);
+  write_sorted(mdst, kp, kp, 0, out_score + (size_t)qg * kp, out_idx + (size_t)qg * kp);
+}
+
 // ---------------------------------------------------------------------------------------------
 // robust exact scan of ONE query by one CTA: running top-k in shared memory.  Used (a) for queries whose candidate
 // list overflowed — called from the select kernel itself, so the common no-overflow case costs no extra launch —
@@ -135,7 +174,8 @@ __host__ __device__ __forceinline__ int inline_exact_bufcap(int k) {
 
 template <int DT>
 __device__ void exact_scan_body(const SimParams& p, int q, int k, int bufcap, uint64_t* buf, float* qs,
-                                long long idx_offset, float* out_score, int32_t* out_idx) {
+                                long long idx_offset, float* out_score, int32_t* out_idx, uint64_t* merge_lists = nullptr,
+                                uint64_t* merge_dst = nullptr) {
   __shared__ int count;
   __shared__ unsigned long long tau;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,8 +217,16 @@ __device__ void exact_scan_body(const SimParams& p, int q, int k, int bufcap, ui
   }
   block_bitonic_sort_desc(buf, bufcap);
   const int got = count < k ? count : k;
-  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, buf, got, k, idx_offset);
-  else write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+  if (p.ex.G > 0 && merge_lists != nullptr) {
+    // the sorted list moves to merge_dst first: merge_lists may alias buf
+    for (int i = threadIdx.x; i < k; i += blockDim.x) merge_dst[i] = i < got ? buf[i] : 0ull;
+    __syncthreads();
+    exchange_and_merge(p.ex, q, merge_dst, got, k, idx_offset, merge_lists, merge_dst, out_score, out_idx);
+  } else if (p.ex.G > 0) {
+    push_sorted_to_peers(p.ex, q, buf, got, k, idx_offset);
+  } else {
+    write_sorted(buf, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+  }
 }
 
 constexpr int kMergeStage = 8192;  // G*k keys the exchange merge stages in shared memory (64 KB)
@@ -235,9 +283,15 @@ __device__ __forceinline__ bool merge_first_phase(const SimParams& p, int q, flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int chunks = p.row_bytes >> 4;
     for (int ri = 0; ri < nredo; ++ri) {
-      const long long tile = ((long long)s_redo[ri] * p.perm_mul) % p.perm_n;
-      const long long row0 = tile * p.tile_rows;
-      long long end = row0 + p.tile_rows;
+      long long row0, end;
+      if (p.range_rows > 0) {  // range mode: slot s = first tile of CTA s
+        row0 = (long long)s_redo[ri] * p.range_rows;
+        end = row0 + p.first_rows;
+      } else {
+        const long long tile = ((long long)s_redo[ri] * p.perm_mul) % p.perm_n;
+        row0 = tile * p.tile_rows;
+        end = row0 + p.tile_rows;
+      }
       if (end > p.n) end = p.n;
       for (long long base = row0 + warp * 4; base < end; base += (long long)nwarps * 4) {
         const int nvalid = (int)((end - base) < 4 ? (end - base) : 4);
@@ -312,7 +366,7 @@ __global__ void __launch_bounds__(kSelectThreads)
     const int bufcap = inline_exact_bufcap(k);
     if (bufcap <= kStageKeys) {  // right here, no extra launch
       __syncthreads();
-      exact_scan_body<DT>(p, q, k, bufcap, stage, qs, idx_offset, out_score, out_idx);
+      exact_scan_body<DT>(p, q, k, bufcap, stage, qs, idx_offset, out_score, out_idx, p.ex.fold ? stage : nullptr, dst);
     } else if (threadIdx.x == 0) {
       ovf[q] = 1u;  // very large k: the separate exact kernel owns this query
     }
@@ -337,15 +391,25 @@ __global__ void __launch_bounds__(kSelectThreads)
     auto key_at = [=](int i) -> unsigned long long { return c[i]; };
     got = block_select_topk(key_at, (int)m, k, dst, kpad, &scr.sel);
   }
-  if (p.ex.G > 0) push_sorted_to_peers(p.ex, q, dst, got, k, idx_offset);
+  if (p.ex.G > 0) exchange_and_merge(p.ex, q, dst, got, k, idx_offset, stage, dst, out_score, out_idx);
   else write_sorted(dst, got, k, idx_offset, out_score + (size_t)q * k, out_idx + (size_t)q * k);
+}
+
+// can the exchange merge run inside the select kernel?  (every select CTA resident, lists fit the staging area)
+bool select_can_fold_merge(int nq_total, int G, int k_push) {
+  static const int on = getenv("RIR_FOLD_MERGE") ? atoi(getenv("RIR_FOLD_MERGE")) : 1;
+  const int kpad = pow2_ceil_int(k_push < 32 ? 32 : k_push);
+  return on != 0 && nq_total <= sm_count() && (long long)G * k_push <= kStageKeys && k_push <= kpad &&
+         select_handles_overflow(k_push);
 }
 
 bool select_handles_overflow(int k) { return inline_exact_bufcap(k) <= kStageKeys; }
 
 int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st) {
-  const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
+  int kk = k < 32 ? 32 : k;
+  if (p.ex.G > 0 && p.ex.k_push > kk) kk = p.ex.k_push;  // a shard shorter than k still merges lists of k_push keys
+  const int kpad = pow2_ceil_int(kk);
   const size_t smem = (size_t)(kpad + kStageKeys) * sizeof(uint64_t) + (size_t)p.d * sizeof(float);
   if (smem > 220 * 1024) {
     set_error("sim_topk(select): k=%d d=%d needs %zu B of shared memory", k, p.d, smem);

@@ -498,6 +498,87 @@ class ShardedDatabase:
         return merge_topk(all_s, all_i)
 
 
+class HostQueryPipeline:
+    """Serving loop for host-resident query batches: `submit(q_host)` enqueues one batch and returns a PendingQuery.
+
+    What the reference call site does per batch (iris_evaluate.py:378-386: CPU fp32 query features -> similarity ->
+    ranking on the host) as a two-stage device pipeline:
+      copy stream : pinned fp32 queries -> H2D -> pack to the shard's dtype  (double-buffered staging)
+      main stream : wait for that copy -> search (local or sharded with peer exchange) -> the top-k is written by the
+                    select / merge kernel straight into pinned host buffers -> completion event
+    With two batches in flight the copy + pack of batch i+1 runs under the scan of batch i and the device never waits
+    for the host's turnaround.  `db` is a Database or a ShardedDatabase (peer exchange enabled when world > 1)."""
+
+    def __init__(self, db, nq: int, k: int, depth: int = 2, path: str = "auto"):
+        self.db = db
+        self.local = db.local if isinstance(db, ShardedDatabase) else db
+        loc = self.local
+        if loc.rescore_rows is not None or loc.dtype == "fp32":
+            raise ValueError("HostQueryPipeline serves bf16 / fp8 shards without a rescoring copy")
+        if isinstance(db, ShardedDatabase) and db.world > 1 and (db._inbox is None or nq > db._nq_max or k > db._k_max):
+            raise ValueError("enable_peer_exchange(nq_max, k_max) first (and keep nq, k within it)")
+        if not (isinstance(db, ShardedDatabase) and db.world > 1) and k > loc.n:
+            raise ValueError(f"k={k} exceeds the database size {loc.n}")
+        self.nq, self.k, self.depth, self.path = int(nq), int(k), int(depth), path
+        dev = loc.rows.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "q32": torch.empty((nq, loc.d), dtype=torch.float32, device=dev),
+                "qr": torch.empty((nq, loc.d), dtype=loc.rows.dtype, device=dev),
+                "qs": torch.empty(nq, dtype=torch.float32, device=dev) if loc.dtype == "fp8" else None,
+                "sc": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                "ix": torch.empty((nq, k), dtype=torch.int32).pin_memory(),
+                "copied": torch.cuda.Event(), "done": None})
+        self._i = 0
+
+    def submit(self, q_host: torch.Tensor) -> PendingQuery:
+        loc, lib = self.local, _lib.load()
+        if q_host.is_cuda or q_host.dtype != torch.float32 or tuple(q_host.shape) != (self.nq, loc.d):
+            raise TypeError(f"expected a float32 CPU tensor [{self.nq}, {loc.d}] (pinned for an asynchronous copy)")
+        slot = self.slots[self._i % self.depth]
+        self._i += 1
+        main = torch.cuda.current_stream(loc.rows.device)
+        dt = _DTYPES[loc.dtype]
+        with torch.cuda.device(loc.rows.device):
+            if slot["done"] is not None:
+                self.copy_stream.wait_event(slot["done"])    # the search that last read this staging slot has finished
+            with torch.cuda.stream(self.copy_stream):
+                slot["q32"].copy_(q_host, non_blocking=True)
+                _lib.check(lib.rir_pack_descriptors(slot["q32"].data_ptr(), self.nq, loc.d, dt, slot["qr"].data_ptr(),
+                                                    None if slot["qs"] is None else slot["qs"].data_ptr(),
+                                                    self.copy_stream.cuda_stream))
+                slot["copied"].record(self.copy_stream)
+            main.wait_event(slot["copied"])
+            k_local = min(self.k, loc.n)
+            check_k_supported(k_local, loc.n)
+            ws = loc.workspace(self.nq, k_local)
+            qs_ptr = None if slot["qs"] is None else slot["qs"].data_ptr()
+            xs_ptr = None if loc.scale is None else loc.scale.data_ptr()
+            try:
+                # pinned host memory is device-addressable (UVA): the kernels store the top-k straight into it
+                if isinstance(self.db, ShardedDatabase) and self.db.world > 1:
+                    sdb = self.db
+                    sdb._epoch += 1
+                    _lib.check(lib.rir_sim_topk_sharded(
+                        slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, self.k,
+                        loc.idx_offset, slot["sc"].data_ptr(), slot["ix"].data_ptr(), ws.data_ptr(), ws.numel(),
+                        PATHS[self.path] | RIR_WS_CLEAN, main.cuda_stream, sdb.world, sdb.rank, sdb._epoch, sdb._nq_max,
+                        sdb._k_max, sdb._peers))
+                else:
+                    _lib.check(lib.rir_sim_topk(
+                        slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, k_local,
+                        loc.idx_offset, slot["sc"].data_ptr(), slot["ix"].data_ptr(), ws.data_ptr(), ws.numel(),
+                        PATHS[self.path] | RIR_WS_CLEAN, main.cuda_stream))
+            except _lib.RirError:
+                loc._drop_workspaces()
+                raise
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(main)
+        return PendingQuery(slot["done"], slot["sc"], slot["ix"], q_host)
+
+
 def pad_topk(sc: torch.Tensor, ix: torch.Tensor, k: int):
     """A shard shorter than k pads its list with (-inf, -1) so every rank contributes [nq, k]."""
     have = sc.shape[1]

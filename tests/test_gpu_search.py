@@ -643,3 +643,46 @@ def test_profile_scan_hook_counts_every_query_group(cuda_device):
     assert all(0.0 < m < 50.0 for m in ms)
     lib.rir_profile_scan_begin()       # disarmed after end: a fresh begin/end with no search records nothing
     assert lib.rir_profile_scan_end(buf, 16, ctypes.byref(n)) == 0 and n.value == 0
+
+
+def test_host_query_pipeline_matches_sync_call(cuda_device):
+    """HostQueryPipeline (copy stream + two batches in flight) returns exactly what the synchronous host call returns,
+    batch after batch, with re-used staging slots."""
+    nq, n, d, k = 70, 100003, 128, 100
+    Q, X, _ = synth.retrieval_set(4 * nq, n, d, seed=606)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    batches = [Q[i * nq:(i + 1) * nq].contiguous().pin_memory() for i in range(4)]
+    want = [tuple(t.clone() for t in db.query_host(b, k)) for b in batches]
+    pipe = rir.HostQueryPipeline(db, nq, k, depth=2)
+    pending, got = [], []
+    for rep in range(3):
+        for i, b in enumerate(batches):
+            pending.append((i, pipe.submit(b)))
+            if len(pending) == 2:
+                j, h = pending.pop(0)
+                sc, ix = h.result()
+                got.append((j, sc.clone(), ix.clone()))
+    for j, h in pending:
+        sc, ix = h.result()
+        got.append((j, sc.clone(), ix.clone()))
+    assert len(got) == 12
+    for j, sc, ix in got:
+        assert torch.equal(ix, want[j][1]) and torch.equal(sc, want[j][0])
+
+
+@pytest.mark.parametrize("n", [125916, 76000, 100003, 251831])
+def test_fused_scan_range_mode_idle_tail_ctas(cuda_device, n):
+    """Range mode gives every CTA ceil(n / 148) rows rounded up to 32: for these sizes the last CTA(s) own NO real row.
+    Their first-phase slots must read as empty — after a search on another database left real keys in the workspace."""
+    nq, d, k = 70, 64, 100
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=n)
+    db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
+    qr, _ = db.pack_queries(Q.to(cuda_device))
+    # poison the workspace's sample-key region with plausible but foreign keys: a search over a database of near-duplicates
+    big = rir.Database(db.rows.clone(), None, "bf16")
+    big.rows[: 148 * 300] = qr[0]
+    big._ws = db._ws
+    db.workspace(nq, k)
+    big.search(qr, None, k)
+    sc, ix = db.search(qr, None, k, path="mma")
+    _check(sc, ix, qr.float().cpu(), db.rows.float().cpu(), k, 1e-3)
