@@ -330,8 +330,11 @@ def run_ours(args):
         out_i = torch.empty((nq, k), dtype=torch.int32).pin_memory()
         host_call = world == 1 or exchange.startswith("nvlink")
 
+        res_out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
+        peer_or_single = world == 1 or exchange.startswith("nvlink")
+
         def step_resident():
-            return sdb.search(qr, qs, k, path=args.path)
+            return sdb.search(qr, qs, k, path=args.path, out=res_out if peer_or_single else None)
 
         def step_e2e():
             if host_call:  # ONE C-ABI call on host buffers (rir_search_host) + a stream synchronise

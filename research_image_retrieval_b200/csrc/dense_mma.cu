@@ -208,7 +208,7 @@ static int launch_dense_nt(const DensePlan& pl, const void* A12, long long M, co
   if (int e = make_rowmajor_map(&b1, B, N, Kp, RIR_BF16, kDN)) return e;
   if (int e = make_rowmajor_map(&b2, B + (size_t)N * Kp * 2, N, Kp, RIR_BF16, kDN)) return e;
   const size_t smem = (size_t)kDStages * kDStageBytes + sizeof(DenseTail);
-  RIR_CUDA_OK(cudaFuncSetAttribute(dense_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(dense_nt_kernel, smem));
   RIR_CUDA_OK(launch_pdl(dense_nt_kernel, dim3((unsigned)pl.mt, (unsigned)pl.nt, (unsigned)pl.S), dim3(kDThreads), smem, st,
                          pl.g, a1, a2, b1, b2, partial));
   RIR_LAUNCH_OK();

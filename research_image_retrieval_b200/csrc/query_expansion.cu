@@ -136,14 +136,14 @@ extern "C" int rir_aqe_finalize(const void* Q, int dtype, const float* q_scale, 
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)d * sizeof(float);
   if (dtype == RIR_BF16) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(aqe_finalize_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(aqe_finalize_kernel<RIR_BF16>, smem));
     aqe_finalize_kernel<RIR_BF16><<<nq, 256, smem, st>>>(Q, q_scale, acc, d, out_f32, out_q, out_scale);
   } else if (dtype == RIR_FP8E4M3) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(aqe_finalize_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(aqe_finalize_kernel<RIR_FP8E4M3>, smem));
     aqe_finalize_kernel<RIR_FP8E4M3><<<nq, 256, smem, st>>>(Q, q_scale, acc, d, out_f32, out_q, out_scale);
   } else if (dtype == RIR_F32) {
     RIR_REQUIRE(out_q == nullptr, "aqe_finalize: out_q must be NULL for fp32 queries (use out_f32)");
-    RIR_CUDA_OK(cudaFuncSetAttribute(aqe_finalize_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(aqe_finalize_kernel<RIR_F32>, smem));
     aqe_finalize_kernel<RIR_F32><<<nq, 256, smem, st>>>(Q, q_scale, acc, d, out_f32, out_q, out_scale);
   } else {
     set_error("aqe_finalize: bad dtype %d", dtype);

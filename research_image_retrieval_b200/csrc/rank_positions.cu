@@ -173,7 +173,7 @@ static int rank_count_dt(const SimParams& p, long long idx_offset, const unsigne
     set_error("rank_count: d=%d needs %zu B of shared memory", p.d, smem);
     return RIR_E_ARG;
   }
-  RIR_CUDA_OK(cudaFuncSetAttribute(rank_count_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(rank_count_kernel<DT>, smem));
   const int groups = (p.nq + kRQ - 1) / kRQ;
   long long gx = (2ll * sm_count() + groups - 1) / groups;
   if (gx < 1) gx = 1;

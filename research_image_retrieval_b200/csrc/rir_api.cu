@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "sim_topk.cuh"
 #include "topk_select.cuh"
@@ -46,6 +47,22 @@ int check_arch() {
     return RIR_E_ARCH;
   }
   return RIR_OK;
+}
+
+// (kernel, device) -> largest dynamic shared memory size already granted with cudaFuncSetAttribute
+int dyn_smem_granted(const void* kern, int dev, int bytes, bool record) {
+  struct Entry { const void* k; int dev, bytes; };
+  static Entry table[256];
+  static int used = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (table[i].k == kern && table[i].dev == dev) {
+      if (record && bytes > table[i].bytes) table[i].bytes = bytes;
+      return table[i].bytes >= bytes ? 1 : 0;
+    }
+  if (record && used < 256) table[used++] = Entry{kern, dev, bytes};
+  return 0;
 }
 
 bool pdl_enabled() {

@@ -46,6 +46,23 @@ int sm_count();
     }                                                                                       \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a driver call per launch: remember, per kernel and device, the
+// largest size already granted and only raise it.  (The search step is two launches of ~50 us each at 8-way sharding:
+// a microsecond of host time per launch is a percent of the step.)
+int dyn_smem_granted(const void* kern, int dev, int bytes, bool record);  // rir_api.cu: (kernel, device) -> bytes table
+#ifdef __CUDACC__
+template <class K>
+static inline cudaError_t ensure_dyn_smem(K kern, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (dyn_smem_granted(key, dev, (int)bytes, false)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) dyn_smem_granted(key, dev, (int)bytes, true);
+  return e;
+}
+#endif
+
 // Launch with programmatic stream serialization (PDL) unless RIR_PDL=0: the kernel's CTAs may be scheduled while the
 // previous kernel of the stream drains; the kernel itself calls pdl_wait() before touching global memory.
 bool pdl_enabled();

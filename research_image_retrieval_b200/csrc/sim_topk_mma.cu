@@ -911,8 +911,7 @@ static int launch_mma_t(const SimParams& p, const MmaGeom& g, const CUtensorMap&
   cfg.blockDim = dim3(128 + 128 * MB);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  RIR_CUDA_OK(cudaFuncSetAttribute(sim_mma_kernel<DT, MB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem_bytes));
+  RIR_CUDA_OK(ensure_dyn_smem(sim_mma_kernel<DT, MB, TWO>, smem_bytes));
   auto launch_with = [&](bool coop, bool pdl) -> cudaError_t {
     cudaLaunchAttribute attr[3];
     int na = 0;
@@ -1011,7 +1010,7 @@ static int max_active_clusters4() {  // clusters of 4 CTAs of the pair kernel th
   const size_t smem_bytes = (size_t)nslots * (kBBytes / 2) + (size_t)nslots * kABytes * MB + sizeof(MmaSmemTail);
   auto kern = sim_mma_kernel<RIR_BF16, MB, 1>;
   int n = 0;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) == cudaSuccess) {
+  if (ensure_dyn_smem(kern, smem_bytes) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(4 * 64);
     cfg.blockDim = dim3(128 + 128 * MB);

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kSelectThreads) sample_threshold_kernel(const 
 int launch_sample_threshold(const SimParams& p, int nq_total, int k, cudaStream_t st) {
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
   const size_t smem = (size_t)kpad * sizeof(uint64_t);
-  RIR_CUDA_OK(cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(sample_threshold_kernel, smem));
   sample_threshold_kernel<<<nq_total, kSelectThreads, smem, st>>>(p, k, kpad);
   RIR_LAUNCH_OK();
   return RIR_OK;
@@ -111,11 +111,13 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
     if (key != 0ull) out = make_key(key_score(key), (uint32_t)((long long)key_index(key) + idx_offset));
     exchange_keys(ex.inbox[g], ex, b, ex.rank, qg)[j] = out;
   }
-  __threadfence_system();
+  // The key stores of all threads happen-before the flag store through the block barrier, and a release at system
+  // scope is cumulative over that order (the pattern of a cooperative-groups grid sync): ONE fence + release store by
+  // the flag-writing threads instead of a system-scope fence in all 512 (each of which waits out an NVLink round trip).
   __syncthreads();
   if ((int)threadIdx.x < ex.G) {
     uint32_t* f = exchange_flag(ex.inbox[threadIdx.x], ex, b, ex.rank, qg);
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(ex.epoch) : "memory");
+    asm volatile("fence.acq_rel.sys;\n\tst.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(ex.epoch) : "memory");
   }
 }
 
@@ -417,13 +419,13 @@ int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long
   }
   const dim3 grid((unsigned)nq_total), block((unsigned)select_threads());
   if (dtype == RIR_BF16) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(final_select_kernel<RIR_BF16>, smem));
     RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_BF16>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   } else if (dtype == RIR_FP8E4M3) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(final_select_kernel<RIR_FP8E4M3>, smem));
     RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_FP8E4M3>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   } else {
-    RIR_CUDA_OK(cudaFuncSetAttribute(final_select_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(final_select_kernel<RIR_F32>, smem));
     RIR_CUDA_OK(launch_pdl(final_select_kernel<RIR_F32>, grid, block, smem, st, p, k, kpad, idx_offset, out_score, out_idx, ovf));
   }
   RIR_LAUNCH_OK();
@@ -461,13 +463,13 @@ int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long l
     return RIR_E_ARG;
   }
   if (dtype == RIR_BF16) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(exact_scan_kernel<RIR_BF16>, smem));
     exact_scan_kernel<RIR_BF16><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
   } else if (dtype == RIR_FP8E4M3) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_FP8E4M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(exact_scan_kernel<RIR_FP8E4M3>, smem));
     exact_scan_kernel<RIR_FP8E4M3><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
   } else if (dtype == RIR_F32) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(exact_scan_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(exact_scan_kernel<RIR_F32>, smem));
     exact_scan_kernel<RIR_F32><<<nq_total, kExactThreads, smem, st>>>(p, k, bufcap, idx_offset, out_score, out_idx, ovf);
   } else {
     set_error("sim_topk(exact): unsupported dtype %d", dtype);
@@ -619,7 +621,7 @@ int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, i
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
   const int m = ex.G * k;
   const size_t smem = (size_t)(kpad + (m <= kMergeStage ? m : 0)) * sizeof(uint64_t);
-  RIR_CUDA_OK(cudaFuncSetAttribute(merge_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(merge_exchange_kernel, smem));
   RIR_CUDA_OK(launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3((unsigned)select_threads()), smem, st, ex, k, kpad,
                          out_score, out_idx));
   RIR_LAUNCH_OK();
@@ -646,11 +648,11 @@ extern "C" int rir_rescore_topk(const void* Q, const void* X, int dtype, const f
   RIR_REQUIRE(smem <= 220 * 1024, "rescore_topk: k_in/k/d too large for shared memory");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == RIR_BF16) {
-    RIR_CUDA_OK(cudaFuncSetAttribute(rescore_kernel<RIR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(rescore_kernel<RIR_BF16>, smem));
     rescore_kernel<RIR_BF16><<<nq, kExactThreads, smem, st>>>(Q, X, q_scale, x_scale, n_local, idx_offset, d, ix_in, k_in, k,
                                                              kpad, out_score, out_idx);
   } else {
-    RIR_CUDA_OK(cudaFuncSetAttribute(rescore_kernel<RIR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RIR_CUDA_OK(ensure_dyn_smem(rescore_kernel<RIR_F32>, smem));
     rescore_kernel<RIR_F32><<<nq, kExactThreads, smem, st>>>(Q, X, q_scale, x_scale, n_local, idx_offset, d, ix_in, k_in, k,
                                                             kpad, out_score, out_idx);
   }
@@ -674,7 +676,7 @@ extern "C" int rir_merge_topk(const float* sc, const int32_t* ix, int G, int nq,
   if (nq == 0) return RIR_OK;
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
   const size_t smem = (size_t)(kpad + ((long long)G * k <= kMergeRankMax ? G * k : 0)) * sizeof(uint64_t);
-  RIR_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(merge_topk_kernel, smem));
   merge_topk_kernel<<<nq, kSelectThreads, smem, (cudaStream_t)stream>>>(sc, ix, G, nq, k, kpad, out_sc, out_ix);
   RIR_LAUNCH_OK();
   return RIR_OK;

@@ -250,7 +250,7 @@ static int launch_stream_t(const SimParams& p, cudaStream_t st) {
     g.nstages_total = (p.n + g.rows_per_stage - 1) / g.rows_per_stage;
   const size_t smem = (size_t)stages * g.stage_bytes + fixed;
   auto kern = sim_stream_kernel<DT, QB, RPW>;
-  RIR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RIR_CUDA_OK(ensure_dyn_smem(kern, smem));
   long long grid = g.nstages_total < (long long)sm_count() ? g.nstages_total : (long long)sm_count();
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, kStreamThreads, smem, st>>>(p, g);

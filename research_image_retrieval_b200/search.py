@@ -185,12 +185,13 @@ class Database:
             raise ValueError(f"unsupported search shape nq={nq} n={self.n} d={self.d} k={k}")
         return self._workspace("sim", need)
 
-    def search(self, q_rows: torch.Tensor, q_scale: Optional[torch.Tensor], k: int, path: str = "auto"):
-        """Exact local top-k.  Returns (scores [nq, k] fp32, idx [nq, k] int32 GLOBAL indices) on the GPU."""
+    def search(self, q_rows: torch.Tensor, q_scale: Optional[torch.Tensor], k: int, path: str = "auto", out=None):
+        """Exact local top-k.  Returns (scores [nq, k] fp32, idx [nq, k] int32 GLOBAL indices) on the GPU
+        (`out` = (scores, idx) tensors to fill instead of allocating)."""
         try:
             return sim_topk(q_rows, self.rows, k, dtype=self.dtype, q_scale=q_scale, x_scale=self.scale,
                             idx_offset=self.idx_offset, path=path, workspace=self.workspace(q_rows.shape[0], k),
-                            ws_clean=True)
+                            ws_clean=True, out=out)
         except _lib.RirError:
             self._drop_workspaces()
             raise
@@ -440,14 +441,17 @@ class ShardedDatabase:
             lib.rir_peer_free(self._inbox)
         self._inbox, self._peers, self._opened = None, None, []
 
-    def _search_peer(self, q_rows, q_scale, k: int, path: str):
+    def _search_peer(self, q_rows, q_scale, k: int, path: str, out=None):
         lib = _lib.load()
         loc = self.local
         nq = q_rows.shape[0]
         k_local = min(k, loc.n)
         check_k_supported(k_local, loc.n)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=loc.rows.device)
-        ix = torch.empty((nq, k), dtype=torch.int32, device=loc.rows.device)
+        if out is None:
+            sc = torch.empty((nq, k), dtype=torch.float32, device=loc.rows.device)
+            ix = torch.empty((nq, k), dtype=torch.int32, device=loc.rows.device)
+        else:
+            sc, ix = out
         ws = loc.workspace(nq, k_local)
         self._epoch += 1
         with torch.cuda.device(loc.rows.device):
@@ -479,7 +483,7 @@ class ShardedDatabase:
     def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto"):
         return self.query_host_async(q_host, k, out=out, path=path).result()
 
-    def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto"):
+    def search(self, q_rows, q_scale, k: int, path: str = "auto", exchange: str = "auto", out=None):
         """exchange: "auto" = peer memory when enabled and the batch fits the inbox, else all-gather; "nccl" forces the
         all-gather + merge path.  Collective: every rank must take the same branch, so the choice depends only on
         arguments that are identical on all ranks (nq, k, the inbox shape) — never on rank-local tensor state."""
@@ -488,9 +492,10 @@ class ShardedDatabase:
         if q_scale is not None:
             q_scale = q_scale.contiguous()
         if exchange != "nccl" and self._inbox is not None and 0 < q_rows.shape[0] <= self._nq_max and k <= self._k_max:
-            return self._search_peer(q_rows, q_scale, k, path)
+            return self._search_peer(q_rows, q_scale, k, path, out=out)
         k_local = min(k, self.local.n)
-        sc, ix = self.local.search(q_rows, q_scale, k_local, path=path)
+        sc, ix = self.local.search(q_rows, q_scale, k_local, path=path,
+                                   out=out if (self.world == 1 and k_local == k) else None)
         sc, ix = pad_topk(sc, ix, k)
         if self.world == 1:
             return sc, ix

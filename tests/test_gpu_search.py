@@ -678,11 +678,18 @@ def test_fused_scan_range_mode_idle_tail_ctas(cuda_device, n):
     Q, X, _ = synth.retrieval_set(nq, n, d, seed=n)
     db = rir.Database.from_descriptors(X.to(cuda_device), "bf16")
     qr, _ = db.pack_queries(Q.to(cuda_device))
-    # poison the workspace's sample-key region with plausible but foreign keys: a search over a database of near-duplicates
-    big = rir.Database(db.rows.clone(), None, "bf16")
-    big.rows[: 148 * 300] = qr[0]
-    big._ws = db._ws
-    db.workspace(nq, k)
-    big.search(qr, None, k)
+    # poison the workspace: first search a LARGER database through the same workspace whose extra rows (exactly the
+    # ranges of the CTAs that are idle for `db`) are copies of every query — their first-phase slots then hold keys
+    # with score ~1.0, far above anything in `db`
+    per = -(-n // 148)
+    R = -(-per // 32) * 32
+    if R % 256 and R % 256 < 64:
+        R += 64 - R % 256
+    n_big = R * 148
+    assert n_big - n >= R, "this size leaves no idle CTA: pick another n"
+    extra = qr[torch.arange(n_big - n, device=cuda_device) % nq]
+    big = rir.Database(torch.cat([db.rows, extra]), None, "bf16")
+    big.search(qr, None, k, path="mma")
+    db._ws = big._ws
     sc, ix = db.search(qr, None, k, path="mma")
     _check(sc, ix, qr.float().cpu(), db.rows.float().cpu(), k, 1e-3)
