@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--sync-exchange", action="store_true")  # N > 1: keep the merge on the search's own stream
     ap.add_argument("--no-parity", action="store_true")   # skip the in-process parity block
     ap.add_argument("--no-extras", action="store_true")   # skip the 1-query / 1024-query points
     return ap.parse_args()
@@ -333,8 +334,26 @@ def run_ours(args):
         res_out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
         peer_or_single = world == 1 or exchange.startswith("nvlink")
 
+        res_out2 = (torch.empty_like(res_out[0]), torch.empty_like(res_out[1]))
+        state = {"i": 0, "prev": None}
+        async_exchange = world > 1 and exchange.startswith("nvlink") and not args.sync_exchange
+
         def step_resident():
+            if async_exchange:
+                # the merge of step i runs on the exchange's side stream next to the scan of step i+1; this stream
+                # waits for the merge of step i-1 (its results are consumed now) — every step's result is joined
+                h = sdb.search_async(qr, qs, k, path=args.path, out=res_out if state["i"] & 1 == 0 else res_out2)
+                state["i"] += 1
+                if state["prev"] is not None:
+                    state["prev"].wait()
+                state["prev"] = h
+                return h
             return sdb.search(qr, qs, k, path=args.path, out=res_out if peer_or_single else None)
+
+        def drain_resident():
+            if state["prev"] is not None:
+                state["prev"].wait()
+                state["prev"] = None
 
         def step_e2e():
             if host_call:  # ONE C-ABI call on host buffers (rir_search_host) + a stream synchronise
@@ -355,6 +374,8 @@ def run_ours(args):
             marks[0].record()
             for i in range(n_steps):
                 fn()
+                if i == n_steps - 1 and fn is step_resident:
+                    drain_resident()          # the last step's merge is inside the timed region too
                 marks[i + 1].record()
             sync_all()
             scan = None
@@ -374,6 +395,7 @@ def run_ours(args):
 
         for _ in range(n_warm):
             step_resident()
+        drain_resident()
         ms, per, scan = timed(step_resident, True)
         res = {"ms": ms, "per_step": per, "scan_ms_per_step": sum(scan) / n_steps if scan else None,
                "scan_launches_per_step": (len(scan) / n_steps) if scan else 0, "qr": qr, "qs": qs}
@@ -423,7 +445,10 @@ def run_ours(args):
             per_group = 4                                   # sample, threshold, scan, select
         else:
             per_group = 2                                   # fused scan + select
-        return groups * per_group + (1 if world > 1 else 0)  # + exchange merge
+        # + the exchange merge: its own kernel on the side stream (asynchronous exchange) or for batches beyond one CTA
+        # per SM; otherwise folded into the select kernel
+        merge = 0 if world == 1 else (1 if (not args.sync_exchange or nq > 148 or args.exchange == "nccl") else 0)
+        return groups * per_group + merge
 
     def roofline_of(nq, scan_ms):
         flops = 2.0 * nq * n_local * args.d
@@ -471,7 +496,12 @@ def run_ours(args):
     if not args.no_parity:
         nqc = min(8, args.nq)
         qr, qs = head["qr"], head["qs"]
-        sc_p, ix_p = sdb.search(qr, qs, k, path=args.path)            # the path that was timed
+        if world > 1 and exchange.startswith("nvlink") and not args.sync_exchange:
+            sc_p, ix_p = sdb.search_async(qr, qs, k, path=args.path).wait()   # the path that was timed
+            sc_s, ix_s = sdb.search(qr, qs, k, path=args.path)                # and the in-stream-order flavour of it
+            assert torch.equal(ix_p, ix_s) and torch.equal(sc_p, sc_s), "asynchronous exchange != synchronous exchange"
+        else:
+            sc_p, ix_p = sdb.search(qr, qs, k, path=args.path)            # the path that was timed
         peer_eq_nccl = None
         if world > 1 and exchange.startswith("nvlink"):
             sc_n, ix_n = sdb.search(qr, qs, k, path=args.path, exchange="nccl")
@@ -522,7 +552,11 @@ def run_ours(args):
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": head["ms"] / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
-            "impl_detail": {"path": args.path, "exchange": exchange},
+            "impl_detail": {"path": args.path, "exchange": exchange,
+                            "exchange_mode": None if world == 1 else (
+                                "asynchronous: merge of step i on a side stream under the scan of step i+1, every result "
+                                "joined before the next one is issued (ShardedDatabase.search_async)"
+                                if (exchange.startswith("nvlink") and not args.sync_exchange) else "in stream order")},
             "step_ms": step_stats(head["per_step"]),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.nq * args.d * 4,

@@ -18,6 +18,7 @@ RIR_F32, RIR_BF16, RIR_FP8E4M3 = 0, 1, 2
 RIR_POOL_GEM, RIR_POOL_MAX, RIR_POOL_AVG = 0, 1, 2
 RIR_PATH_AUTO, RIR_PATH_STREAM, RIR_PATH_MMA, RIR_PATH_EXACT = 0, 1, 2, 3
 RIR_WS_CLEAN = 0x100
+RIR_EXCHANGE_ASYNC = 0x200
 RIR_MAP_OK, RIR_MAP_EMPTY_OK, RIR_MAP_NO_POS_RETRIEVED = 0, 1, 2
 
 PATHS = {"auto": RIR_PATH_AUTO, "stream": RIR_PATH_STREAM, "mma": RIR_PATH_MMA, "exact": RIR_PATH_EXACT}
@@ -63,6 +64,8 @@ SIGNATURES = {
     "rir_sim_topk_sharded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
                                      c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int,
                                      ctypes.c_uint32, c_int, c_int, POINTER(c_void_p)]),
+    "rir_exchange_join": (c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
+    "rir_exchange_sync": (c_int, [c_void_p, ctypes.c_uint32]),
     "rir_search_host_workspace": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
     "rir_search_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, ctypes.c_uint32, c_int, c_int,

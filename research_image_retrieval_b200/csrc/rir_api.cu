@@ -232,12 +232,68 @@ extern "C" int rir_sim_topk_workspace_init(void* workspace, size_t workspace_byt
   return RIR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// asynchronous exchange (RIR_EXCHANGE_ASYNC): per inbox, a side stream + events so that the merge of search e runs
+// next to the scan of search e+1 instead of in front of it
+// ---------------------------------------------------------------------------------------------
+struct AsyncExchange {
+  const void* inbox;
+  int dev;
+  cudaStream_t side;
+  cudaEvent_t sel_done[2], merge_done[2];
+  uint32_t epoch[2];  // epoch whose merge merge_done[b] stands for (0 = none yet)
+};
+static std::mutex g_ax_mu;
+static std::vector<AsyncExchange*> g_ax;
+
+static AsyncExchange* ax_find(const void* inbox, bool create) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_ax_mu);
+  for (AsyncExchange* a : g_ax)
+    if (a->inbox == inbox && a->dev == dev) return a;
+  if (!create) return nullptr;
+  AsyncExchange* a = new AsyncExchange();
+  a->inbox = inbox;
+  a->dev = dev;
+  a->epoch[0] = a->epoch[1] = 0u;
+  bool ok = cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&a->sel_done[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&a->merge_done[b], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    delete a;
+    return nullptr;
+  }
+  g_ax.push_back(a);
+  return a;
+}
+
+static void ax_drop(const void* inbox) {
+  std::lock_guard<std::mutex> lock(g_ax_mu);
+  for (size_t i = 0; i < g_ax.size(); ++i)
+    if (g_ax[i]->inbox == inbox) {
+      AsyncExchange* a = g_ax[i];
+      cudaStreamSynchronize(a->side);
+      for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(a->sel_done[b]);
+        cudaEventDestroy(a->merge_done[b]);
+      }
+      cudaStreamDestroy(a->side);
+      delete a;
+      g_ax.erase(g_ax.begin() + i);
+      return;
+    }
+}
+
 static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
                          int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
                          void* workspace, size_t workspace_bytes, int path, void* stream, const Exchange* ex) {
   if (int e = check_arch()) return e;
   const bool ws_clean = (path & RIR_WS_CLEAN) != 0;  // the caller keeps the header invariant: no memset launches
-  path &= ~RIR_WS_CLEAN;
+  const bool ex_async = ex != nullptr && (path & RIR_EXCHANGE_ASYNC) != 0;
+  path &= ~(RIR_WS_CLEAN | RIR_EXCHANGE_ASYNC);
   const int esz = elem_size(dtype);
   RIR_REQUIRE(esz != 0, "sim_topk: dtype must be RIR_F32, RIR_BF16 or RIR_FP8E4M3 (got %d)", dtype);
   RIR_REQUIRE(dtype != RIR_F32 || path != RIR_PATH_MMA, "sim_topk: fp32 descriptors run on the stream path only");
@@ -266,6 +322,7 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     exl = *ex;
     exl.k_push = k_req;
     exl.fold = 0;
+    exl.nq_epoch = nq;
     ex = &exl;
   }
 
@@ -292,7 +349,7 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
   }
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   // one query group whose select CTAs are all co-resident: the select kernel merges the peers' lists itself
-  if (ex && nq <= pl.group && select_can_fold_merge(nq, ex->G, k_req)) exl.fold = 1;
+  if (ex && !ex_async && nq <= pl.group && select_can_fold_merge(nq, ex->G, k_req)) exl.fold = 1;
 
   for (int g0 = 0; g0 < nq; g0 += pl.group) {
     const int gq = (nq - g0) < pl.group ? (nq - g0) : pl.group;
@@ -412,6 +469,22 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     }
   }
   // sharded: every rank's lists are on their way into the inboxes; wait for all G of them and merge
+  if (ex_async) {
+    // on the inbox's side stream, behind this call's select kernels: the caller's stream goes straight on to the next
+    // search; rir_exchange_join / rir_exchange_sync order consumers behind the merge
+    AsyncExchange* a = ax_find(ex->inbox[ex->rank], true);
+    if (a == nullptr) {
+      set_error("sim_topk_sharded: could not create the side stream of the asynchronous exchange");
+      return RIR_E_CUDA;
+    }
+    const int b = (int)(ex->epoch & 1u);
+    RIR_CUDA_OK(cudaEventRecord(a->sel_done[b], st));
+    RIR_CUDA_OK(cudaStreamWaitEvent(a->side, a->sel_done[b], 0));
+    if (int e = launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, a->side, true)) return e;
+    RIR_CUDA_OK(cudaEventRecord(a->merge_done[b], a->side));
+    a->epoch[b] = ex->epoch;
+    return RIR_OK;
+  }
   if (ex && !ex->fold) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
   return RIR_OK;
 }
@@ -441,7 +514,28 @@ extern "C" int rir_peer_alloc(size_t bytes, void** ptr) {
 }
 
 extern "C" int rir_peer_free(void* ptr) {
-  if (ptr) RIR_CUDA_OK(cudaFree(ptr));
+  if (ptr) {
+    ax_drop(ptr);
+    RIR_CUDA_OK(cudaFree(ptr));
+  }
+  return RIR_OK;
+}
+
+extern "C" int rir_exchange_join(const void* own_inbox, uint32_t epoch, void* stream) {
+  AsyncExchange* a = ax_find(own_inbox, false);
+  if (a == nullptr) return RIR_OK;  // no asynchronous search was issued on this inbox
+  const int b = (int)(epoch & 1u);
+  RIR_REQUIRE(a->epoch[b] == epoch, "exchange_join: epoch %u is not outstanding (parity holds %u)", epoch, a->epoch[b]);
+  RIR_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, a->merge_done[b], 0));
+  return RIR_OK;
+}
+
+extern "C" int rir_exchange_sync(const void* own_inbox, uint32_t epoch) {
+  AsyncExchange* a = ax_find(own_inbox, false);
+  if (a == nullptr) return RIR_OK;
+  const int b = (int)(epoch & 1u);
+  RIR_REQUIRE(a->epoch[b] == epoch, "exchange_sync: epoch %u is not outstanding (parity holds %u)", epoch, a->epoch[b]);
+  RIR_CUDA_OK(cudaEventSynchronize(a->merge_done[b]));
   return RIR_OK;
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import PATHS, RIR_BF16, RIR_F32, RIR_FP8E4M3, RIR_WS_CLEAN
+from ._lib import PATHS, RIR_BF16, RIR_EXCHANGE_ASYNC, RIR_F32, RIR_FP8E4M3, RIR_WS_CLEAN
 
 _DTYPES = {"bf16": RIR_BF16, "fp8": RIR_FP8E4M3, "fp32": RIR_F32}
 _TORCH_DT = {"bf16": torch.bfloat16, "fp32": torch.float32}
@@ -112,17 +112,30 @@ def pack_descriptors(v: torch.Tensor, dtype: str = "bf16"):
 
 
 class PendingQuery:
-    """Handle of an enqueued host-buffer search (Database.query_host_async)."""
+    """Handle of an enqueued search whose results are not yet valid (Database.query_host_async,
+    ShardedDatabase.search_async, HostQueryPipeline.submit).  `.result()` blocks the HOST until they are and returns
+    (scores, idx); `.wait()` makes the current CUDA stream wait instead (device-side consumers)."""
 
-    def __init__(self, event, sc, ix, q_host):
+    def __init__(self, event, sc, ix, keep=None, join=None, sync=None):
         self._event, self._sc, self._ix = event, sc, ix
-        self._q_host = q_host   # keeps the (pinned) query buffer alive until the copy has run
+        self._keep = keep              # keeps input buffers alive until the work that reads them has run
+        self._join, self._sync = join, sync   # asynchronous exchange: the merge lives on the library's side stream
 
     def done(self) -> bool:
-        return self._event.query()
+        return self._event.query() if self._sync is None else False
+
+    def wait(self):
+        if self._join is not None:
+            self._join()
+        else:
+            torch.cuda.current_stream().wait_event(self._event)
+        return self._sc, self._ix
 
     def result(self):
-        self._event.synchronize()
+        if self._sync is not None:
+            self._sync()
+        else:
+            self._event.synchronize()
         return self._sc, self._ix
 
 
@@ -228,7 +241,7 @@ class Database:
                 raise
             done = torch.cuda.Event()
             done.record()
-        return PendingQuery(done, sc, ix, q_host)
+        return PendingQuery(done, sc, ix, keep=q_host)
 
     def query_host(self, q_host: torch.Tensor, k: int, out=None, path: str = "auto", _exchange=None):
         """query_host_async(...).result(): the synchronous host-facing call (`out` to re-use pinned result buffers)."""
@@ -322,7 +335,14 @@ def rank(query_features, gallery_features, k: Optional[int] = None, dtype: str =
 
     Returns an int64 ndarray [k_or_N, nq] — column per query, the layout compute_map consumes
     (utils/evaluate.py:49).  dtype='fp32' keeps the reference arithmetic type; 'bf16'/'fp8' use the tensor-core path.
-    normalize=True applies F.normalize to both sides first (iris_evaluate.py:379-380)."""
+    normalize=True applies F.normalize to both sides first (iris_evaluate.py:379-380).
+
+    Limits (include/rir.h): a FULL ranking (k=None) is produced for galleries of at most 16,384 rows (ROxford / RParis
+    size); larger galleries (e.g. +1M distractors) take a top-k with k <= 8192 — for the revisited protocol over such a
+    gallery use `revisited_map_full`, which needs no ranked list at all.  fp32 on a large gallery: candidates
+    (2k + 64 per query) come from ONE bf16 tensor-core scan, their scores and final order from an fp32 re-score of
+    those rows (rir_rescore_topk) — fp32 scores, exact up to bf16 ties at the over-fetch boundary — instead of
+    ceil(nq / 8) CUDA-core passes over the fp32 rows."""
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     q = torch.as_tensor(query_features).to(device=device, dtype=torch.float32)
@@ -330,10 +350,28 @@ def rank(query_features, gallery_features, k: Optional[int] = None, dtype: str =
     if normalize:
         from .pooling import l2n
         q, g = l2n(q.contiguous()), l2n(g.contiguous())
-    db = Database.from_descriptors(g, dtype)
-    k = clamp_k(k, db.n)
-    qr, qs = db.pack_queries(q)
-    sc, ix = db.search(qr, qs, k, path=path)
+    n = g.shape[0]
+    if n > MAX_FULL_RANK and (k is None or int(k) > MAX_K_FILTER):
+        raise ValueError(f"a gallery of {n} rows is ranked to a top-k with k <= {MAX_K_FILTER} (a full ranking only up to "
+                         f"{MAX_FULL_RANK} rows); for revisited mAP over the whole gallery use revisited_map_full()")
+    if dtype == "fp32" and n > MAX_FULL_RANK and 2 * int(k) + 64 <= MAX_K_FILTER and path == "auto":
+        k = clamp_k(k, n)
+        k_in = 2 * k + 64
+        dbb = Database.from_descriptors(g, "bf16")
+        qr, _ = dbb.pack_queries(q)
+        _, cand = dbb.search(qr, None, k_in)
+        g32, q32 = pack_descriptors(g, "fp32")[0], pack_descriptors(q, "fp32")[0]
+        sc = torch.empty((q.shape[0], k), dtype=torch.float32, device=device)
+        ix = torch.empty((q.shape[0], k), dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().rir_rescore_topk(q32.data_ptr(), g32.data_ptr(), RIR_F32, None, None, q.shape[0], n, 0,
+                                                    g32.shape[1], cand.data_ptr(), k_in, k, sc.data_ptr(), ix.data_ptr(),
+                                                    _lib.stream_ptr()))
+    else:
+        db = Database.from_descriptors(g, dtype)
+        k = clamp_k(k, db.n)
+        qr, qs = db.pack_queries(q)
+        sc, ix = db.search(qr, qs, k, path=path)
     ranks = ix.t().contiguous().to(torch.int64).cpu().numpy()
     if return_scores:
         return ranks, sc.t().contiguous().cpu().numpy()
@@ -441,7 +479,37 @@ class ShardedDatabase:
             lib.rir_peer_free(self._inbox)
         self._inbox, self._peers, self._opened = None, None, []
 
-    def _search_peer(self, q_rows, q_scale, k: int, path: str, out=None):
+    def _exchange_waiters(self, epoch: int, dev):
+        lib, inbox = _lib.load(), self._inbox
+
+        def join():
+            with torch.cuda.device(dev):
+                _lib.check(lib.rir_exchange_join(inbox, epoch, _lib.stream_ptr()))
+
+        def sync():
+            with torch.cuda.device(dev):
+                _lib.check(lib.rir_exchange_sync(inbox, epoch))
+        return join, sync
+
+    def search_async(self, q_rows, q_scale, k: int, path: str = "auto", out=None) -> PendingQuery:
+        """Sharded search with the exchange OFF the critical path (RIR_EXCHANGE_ASYNC): this rank's scan + select run
+        on the current stream; the merge that waits for the peers' lists runs on a side stream, next to the scan of
+        the FOLLOWING search.  Returns a PendingQuery: call `.wait()` (stream order) or `.result()` (host) before
+        touching the outputs.  Collective; at most two searches outstanding, with distinct `out` buffers."""
+        k = min(int(k), self.n_global)
+        q_rows = q_rows.contiguous()
+        if q_scale is not None:
+            q_scale = q_scale.contiguous()
+        if self.world == 1 or self._inbox is None or not (0 < q_rows.shape[0] <= self._nq_max and k <= self._k_max):
+            sc, ix = self.search(q_rows, q_scale, k, path=path, out=out)
+            ev = torch.cuda.Event()
+            ev.record()
+            return PendingQuery(ev, sc, ix)
+        sc, ix = self._search_peer(q_rows, q_scale, k, path, out=out, flags=RIR_EXCHANGE_ASYNC)
+        join, sync = self._exchange_waiters(self._epoch, self.local.rows.device)
+        return PendingQuery(None, sc, ix, keep=(q_rows, q_scale), join=join, sync=sync)
+
+    def _search_peer(self, q_rows, q_scale, k: int, path: str, out=None, flags: int = 0):
         lib = _lib.load()
         loc = self.local
         nq = q_rows.shape[0]
@@ -460,8 +528,8 @@ class ShardedDatabase:
                     q_rows.data_ptr(), loc.rows.data_ptr(), _DTYPES[loc.dtype],
                     None if q_scale is None else q_scale.data_ptr(), None if loc.scale is None else loc.scale.data_ptr(),
                     nq, loc.n, loc.d, k, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), ws.data_ptr(), ws.numel(),
-                    PATHS[path] | RIR_WS_CLEAN, _lib.stream_ptr(), self.world, self.rank, self._epoch, self._nq_max,
-                    self._k_max, self._peers))
+                    PATHS[path] | RIR_WS_CLEAN | flags, _lib.stream_ptr(), self.world, self.rank, self._epoch,
+                    self._nq_max, self._k_max, self._peers))
             except _lib.RirError:
                 loc._drop_workspaces()
                 raise
@@ -561,6 +629,7 @@ class HostQueryPipeline:
             ws = loc.workspace(self.nq, k_local)
             qs_ptr = None if slot["qs"] is None else slot["qs"].data_ptr()
             xs_ptr = None if loc.scale is None else loc.scale.data_ptr()
+            join = sync = None
             try:
                 # pinned host memory is device-addressable (UVA): the kernels store the top-k straight into it
                 if isinstance(self.db, ShardedDatabase) and self.db.world > 1:
@@ -569,8 +638,9 @@ class HostQueryPipeline:
                     _lib.check(lib.rir_sim_topk_sharded(
                         slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, self.k,
                         loc.idx_offset, slot["sc"].data_ptr(), slot["ix"].data_ptr(), ws.data_ptr(), ws.numel(),
-                        PATHS[self.path] | RIR_WS_CLEAN, main.cuda_stream, sdb.world, sdb.rank, sdb._epoch, sdb._nq_max,
-                        sdb._k_max, sdb._peers))
+                        PATHS[self.path] | RIR_WS_CLEAN | RIR_EXCHANGE_ASYNC, main.cuda_stream, sdb.world, sdb.rank,
+                        sdb._epoch, sdb._nq_max, sdb._k_max, sdb._peers))
+                    join, sync = sdb._exchange_waiters(sdb._epoch, loc.rows.device)   # the merge is on the side stream
                 else:
                     _lib.check(lib.rir_sim_topk(
                         slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, k_local,
@@ -579,9 +649,9 @@ class HostQueryPipeline:
             except _lib.RirError:
                 loc._drop_workspaces()
                 raise
-            slot["done"] = torch.cuda.Event()
+            slot["done"] = torch.cuda.Event()   # scan + select have read the staging slot (and, unsharded, written the top-k)
             slot["done"].record(main)
-        return PendingQuery(slot["done"], slot["sc"], slot["ix"], q_host)
+        return PendingQuery(slot["done"], slot["sc"], slot["ix"], keep=q_host, join=join, sync=sync)
 
 
 def pad_topk(sc: torch.Tensor, ix: torch.Tensor, k: int):

@@ -48,6 +48,19 @@ def main():
             torch.cuda.synchronize()
             assert torch.equal(ix, want_ix), f"case {ci} rep {rep}: peer exchange indices differ from the NCCL path"
             assert torch.equal(sc, want_sc), f"case {ci} rep {rep}: peer exchange scores differ from the NCCL path"
+        # asynchronous exchange (merge on the side stream): two searches outstanding, then mixed with synchronous ones
+        outs = [(torch.empty_like(want_sc), torch.empty_like(want_ix)) for _ in range(2)]
+        pend = []
+        for rep in range(5):
+            pend.append(sdb.search_async(qr, qs, min(k, n), out=outs[rep & 1]))
+            if len(pend) == 2:
+                a_sc, a_ix = pend.pop(0).wait()
+                torch.cuda.current_stream().synchronize()
+                assert torch.equal(a_ix, want_ix) and torch.equal(a_sc, want_sc), f"case {ci} rep {rep}: async exchange differs"
+        a_sc, a_ix = pend.pop(0).result()
+        assert torch.equal(a_ix, want_ix) and torch.equal(a_sc, want_sc), f"case {ci}: async exchange (host sync) differs"
+        sc, ix = sdb.search(qr, qs, min(k, n))                       # synchronous call right behind asynchronous ones
+        assert torch.equal(ix, want_ix) and torch.equal(sc, want_sc), f"case {ci}: sync after async differs"
         # a smaller batch afterwards (stale inbox rows must not leak in)
         q2, s2 = qr[:2].contiguous(), None if qs is None else qs[:2].contiguous()
         sc2, ix2 = sdb.search(q2, s2, min(k, n))

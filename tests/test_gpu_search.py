@@ -693,3 +693,20 @@ def test_fused_scan_range_mode_idle_tail_ctas(cuda_device, n):
     db._ws = big._ws
     sc, ix = db.search(qr, None, k, path="mma")
     _check(sc, ix, qr.float().cpu(), db.rows.float().cpu(), k, 1e-3)
+
+
+def test_rank_fp32_on_a_large_gallery(cuda_device):
+    """rank(dtype='fp32') beyond 16,384 rows: bf16 candidates + fp32 re-score — fp32 scores, reference order; a full
+    ranking of such a gallery is refused with a pointer to revisited_map_full."""
+    nq, n, d, k = 70, 60000, 256, 100
+    Q, X, _ = synth.retrieval_set(nq, n, d, seed=77077)
+    ranks, sc = rir.rank(Q, X, k=k, return_scores=True)
+    assert ranks.shape == (k, nq) and ranks.dtype == np.int64
+    ref_sc, ref_ix = S.topk(Q, X, k)
+    got = ranks.T
+    true_of_got = np.stack([(X[torch.from_numpy(got[r])] @ Q[r]).numpy() for r in range(nq)])
+    np.testing.assert_allclose(sc.T, true_of_got, rtol=1e-5, atol=1e-6)      # fp32 scores
+    ok, msg = S.indices_match_up_to_ties(got, true_of_got, ref_ix, ref_sc, 1e-5)
+    assert ok, msg
+    with pytest.raises(ValueError, match="revisited_map_full"):
+        rir.rank(Q, X)
