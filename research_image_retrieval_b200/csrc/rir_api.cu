@@ -287,6 +287,19 @@ static void ax_drop(const void* inbox) {
     }
 }
 
+// A rank may only PUBLISH epoch e (its select kernel stores into the peers' inboxes) once its own merge of epoch e-1 has
+// read every list: a peer needs this rank's epoch-e lists before it can move on to epoch e+1 and overwrite inbox rows of
+// parity (e-1) & 1.  With the merge in stream order that holds by itself; a merge on the side stream is waited for
+// HERE, by the stream (between scan and select: the scan still overlaps it) — not by spinning CTAs, which would hold
+// the SM resources the merge kernel needs (a 1,024-query select fills the register files: measured dead-lock).
+static int wait_previous_async_merge(const Exchange& ex, cudaStream_t st) {
+  AsyncExchange* a = ax_find(ex.inbox[ex.rank], false);
+  if (a == nullptr) return RIR_OK;
+  const int pb = (int)((ex.epoch - 1u) & 1u);
+  if (a->epoch[pb] != 0u && a->epoch[pb] + 1u == ex.epoch) RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merge_done[pb], 0));
+  return RIR_OK;
+}
+
 static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q_scale, const float* x_scale, int nq,
                          int64_t n_local, int d, int k, int64_t idx_offset, float* out_score, int32_t* out_idx,
                          void* workspace, size_t workspace_bytes, int path, void* stream, const Exchange* ex) {
@@ -322,7 +335,6 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     exl = *ex;
     exl.k_push = k_req;
     exl.fold = 0;
-    exl.nq_epoch = nq;
     ex = &exl;
   }
 
@@ -337,6 +349,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     p.Q = Q; p.X = X; p.q_scale = q_scale; p.x_scale = x_scale;
     p.nq = nq; p.q0 = 0; p.n = n_local; p.d = d; p.row_bytes = d * esz;
     if (ex) p.ex = *ex;
+    if (ex)
+      if (int e = wait_previous_async_merge(*ex, st)) return e;
     if (int e = launch_exact_scan(p, dtype, nq, k, idx_offset, out_score, out_idx, nullptr, st)) return e;
     if (ex) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
     return RIR_OK;
@@ -462,6 +476,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     }
     float* os = out_score + (size_t)g0 * k;
     int32_t* oi = out_idx + (size_t)g0 * k;
+    if (ex && g0 == 0)
+      if (int e = wait_previous_async_merge(*ex, st)) return e;
     if (int e = launch_final_select(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
     if (!pl.scan_all && !select_handles_overflow(k)) {
       // very large k: queries whose candidate list overflowed are redone by the separate exact kernel (no-op otherwise)

@@ -39,23 +39,15 @@ struct Exchange {
   int q_base;       // global query index of this launch's query 0
   int k_push;       // list length every rank publishes (the global k; a shard shorter than k pads with 0 keys)
   int fold;         // 1: the select kernel also waits for the peers' lists and merges (no separate merge launch)
-  int nq_epoch;     // queries of this epoch (the merge that handles the last of them publishes "epoch complete")
   unsigned long long* inbox[kMaxPeers];  // inbox of rank g as mapped in THIS process
 };
 __host__ __device__ __forceinline__ size_t exchange_key_slots(int G, int nq_max, int k_max) {
   return (size_t)2 * G * nq_max * k_max;
 }
 __host__ __device__ __forceinline__ size_t exchange_bytes(int G, int nq_max, int k_max) {
-  // keys | flags | merge progress (two words: queries merged in the current epoch, last completely merged epoch)
-  return exchange_key_slots(G, nq_max, k_max) * 8 + (size_t)2 * G * nq_max * 4 + 64;
+  return exchange_key_slots(G, nq_max, k_max) * 8 + (size_t)2 * G * nq_max * 4;
 }
-// Merge progress of THIS rank (in its own inbox): [0] = queries merged so far in the running epoch, [1] = last epoch
-// whose merge has read every list.  A rank's select kernel may only publish epoch e once its own merge of epoch e-1
-// is complete: that is what keeps a peer (which needs this rank's epoch-e lists before it can move on to epoch e+1)
-// from overwriting inbox rows of parity (e-1) & 1 that are still being read — whatever stream the merge runs on.
-__host__ __device__ __forceinline__ uint32_t* exchange_progress(unsigned long long* inbox, const Exchange& ex) {
-  return reinterpret_cast<uint32_t*>(inbox + exchange_key_slots(ex.G, ex.nq_max, ex.k_max)) + (size_t)2 * ex.G * ex.nq_max;
-}
+
 // keys of (parity b, source rank g, query q) inside an inbox
 __host__ __device__ __forceinline__ unsigned long long* exchange_keys(unsigned long long* inbox, const Exchange& ex,
                                                                       int b, int g, int q) {

@@ -104,21 +104,6 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
   const int b = (int)(ex.epoch & 1u);
   const int qg = ex.q_base + q;
   const int kp = ex.k_push;
-  if (threadIdx.x == 0) {  // own merge of the previous epoch complete?  (see exchange_progress)
-    const uint32_t* done = exchange_progress(ex.inbox[ex.rank], ex) + 1;
-    const long long t0 = clock64();
-    while (true) {
-      uint32_t v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
-      if (v + 1u >= ex.epoch) break;
-      __nanosleep(100);
-      if (clock64() - t0 > 20000000000ll) {
-        printf("librir: rank %d: merge of epoch %u never completed (at %u)\n", ex.rank, ex.epoch - 1u, v);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
   for (int i = threadIdx.x; i < ex.G * kp; i += blockDim.x) {
     const int g = i / kp, j = i - g * kp;
     const uint64_t key = (j < got && j < k) ? dst[j] : 0ull;
@@ -133,19 +118,6 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
   if ((int)threadIdx.x < ex.G) {
     uint32_t* f = exchange_flag(ex.inbox[threadIdx.x], ex, b, ex.rank, qg);
     asm volatile("fence.acq_rel.sys;\n\tst.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(ex.epoch) : "memory");
-  }
-}
-
-// one query of this epoch has been merged (its inbox rows are no longer needed); the last one publishes the epoch
-__device__ __forceinline__ void merge_report_done(const Exchange& ex) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t* prog = exchange_progress(ex.inbox[ex.rank], ex);
-    __threadfence();
-    if (atomicAdd(&prog[0], 1u) + 1u == (uint32_t)ex.nq_epoch) {
-      prog[0] = 0u;
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog + 1), "r"(ex.epoch) : "memory");
-    }
   }
 }
 
@@ -186,7 +158,6 @@ __device__ __forceinline__ void exchange_and_merge(const Exchange& ex, int q, co
   __syncthreads();
   block_merge_sorted_lists(lists, ex.G, kp, mdst);
   write_sorted(mdst, kp, kp, 0, out_score + (size_t)qg * kp, out_idx + (size_t)qg * kp);
-  merge_report_done(ex);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -640,12 +611,10 @@ __global__ void __launch_bounds__(kSelectThreads)
     __syncthreads();
     block_merge_sorted_lists(lists, ex.G, k, dst);
     write_sorted(dst, k, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
-    merge_report_done(ex);
     return;
   }
   const int got = block_select_topk(key_at, m, k, dst, kpad, &scr);
   write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
-  merge_report_done(ex);
 }
 
 int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st,
