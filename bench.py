@@ -366,17 +366,29 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
             return out_s, out_i
 
+        SAMPLE = 4   # every 4th step carries the scan-kernel events and a step mark (see rir_profile_scan_pause)
+
         def timed(fn, profile_scan):
-            marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+            marks = [(0, torch.cuda.Event(enable_timing=True))]
+            e_end = torch.cuda.Event(enable_timing=True)
             sync_all()
             if profile_scan:
                 lib.rir_profile_scan_begin()
-            marks[0].record()
+            marks[0][1].record()
+            sampled = 0
             for i in range(n_steps):
+                if profile_scan:
+                    lib.rir_profile_scan_pause(0 if i % SAMPLE == 0 else 1)
+                    sampled += 1 if i % SAMPLE == 0 else 0
                 fn()
                 if i == n_steps - 1 and fn is step_resident:
                     drain_resident()          # the last step's merge is inside the timed region too
-                marks[i + 1].record()
+                if (i + 1) % SAMPLE == 0 and i + 1 < n_steps:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    marks.append((i + 1, ev))
+            e_end.record()
+            marks.append((n_steps, e_end))
             sync_all()
             scan = None
             if profile_scan:
@@ -385,24 +397,25 @@ def run_ours(args):
                 cnt = ctypes.c_int(0)
                 _lib.check(lib.rir_profile_scan_end(buf, cap, ctypes.byref(cnt)))
                 scan = [float(buf[i]) for i in range(min(cnt.value, cap))]
-            ms = marks[0].elapsed_time(marks[-1])
-            per = [marks[i].elapsed_time(marks[i + 1]) for i in range(n_steps)]
+            ms = marks[0][1].elapsed_time(e_end)
+            per = [a[1].elapsed_time(b[1]) / (b[0] - a[0]) for a, b in zip(marks[:-1], marks[1:])]  # ms per step, per window
             if world > 1:
                 t = torch.tensor([ms], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
-            return ms, per, scan
+            return ms, per, scan, sampled
 
         for _ in range(n_warm):
             step_resident()
         drain_resident()
-        ms, per, scan = timed(step_resident, True)
-        res = {"ms": ms, "per_step": per, "scan_ms_per_step": sum(scan) / n_steps if scan else None,
-               "scan_launches_per_step": (len(scan) / n_steps) if scan else 0, "qr": qr, "qs": qs}
+        ms, per, scan, sampled = timed(step_resident, True)
+        res = {"ms": ms, "per_step": per, "scan_ms_per_step": sum(scan) / sampled if scan else None,
+               "scan_launches_per_step": (len(scan) / sampled) if scan else 0, "scan_steps_sampled": sampled,
+               "qr": qr, "qs": qs}
         if with_e2e:
             for _ in range(3):
                 step_e2e()
-            res["ms_e2e"], res["per_step_e2e"], _ = timed(step_e2e, False)
+            res["ms_e2e"], res["per_step_e2e"], _, _ = timed(step_e2e, False)
             if host_call:
                 # the serving loop (HostQueryPipeline): the same copies every step, but two batches in flight and the
                 # H2D + pack of step i+1 on a copy stream under the scan of step i — step i+1 is enqueued before the
@@ -496,6 +509,9 @@ def run_ours(args):
     stream_path = args.path == "stream" or (args.path == "auto" and args.nq <= 2 and n_local < 2 * 148 * 256)
     roofline = roofline_of(args.nq, head["scan_ms_per_step"])
     roofline["kernel"] = "sim_stream_kernel (scan pass)" if stream_path else "sim_mma_kernel (fused sample + scan)"
+    roofline["kernel_ms_source"] = (f"CUDA events around the scan launch on its stream, every 4th step of the timed region "
+                                    f"({head['scan_steps_sampled']} of {steps} steps; an event pair per step would sit between "
+                                    "PDL-chained kernels and cost several percent of a sharded step)")
     roofline["traffic"] = None  # dram bytes of one scan launch from the committed ncu capture of the SAME configuration
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -573,7 +589,7 @@ def run_ours(args):
                                 "asynchronous: merge of step i on a side stream under the scan of step i+1, every result "
                                 "joined before the next one is issued (ShardedDatabase.search_async)"
                                 if (exchange.startswith("nvlink") and not args.sync_exchange) else "in stream order")},
-            "step_ms": step_stats(head["per_step"]),
+            "step_ms": dict(step_stats(head["per_step"]), note="ms per step over 4-step windows of the timed region"),
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": kernels_per_step(args.nq) * steps,

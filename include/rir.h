@@ -176,6 +176,10 @@ int rir_sim_topk_workspace_init(void* workspace, size_t workspace_bytes, void* s
  * scan launches since begin in *n_launches and the duration of launch i (milliseconds) in ms_out[i], i < cap. */
 int rir_profile_scan_begin(void);
 int rir_profile_scan_end(float* ms_out, int cap, int* n_launches);
+/* Sampled profiling: while paused (non-zero) an armed thread records nothing.  An event record between two kernels
+ * costs a few microseconds of stream time and breaks their programmatic-dependent-launch overlap — at 8-way sharding
+ * that is several percent of a step — so bench.py brackets only every 4th step's scan. */
+int rir_profile_scan_pause(int paused);
 
 /* Development hook: event timeline of the tcgen05 scan.  dev_buf = device buffer of (1 + 2 * cap_events) uint64, zeroed
  * by the caller; the following rir_sim_topk calls of THIS host thread append (meta, %globaltimer ns) pairs —

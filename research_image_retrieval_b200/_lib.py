@@ -49,6 +49,7 @@ SIGNATURES = {
     "rir_sim_topk_workspace_init": (c_int, [c_void_p, c_size_t, c_void_p]),
     "rir_profile_scan_begin": (c_int, []),
     "rir_profile_scan_end": (c_int, [POINTER(c_float), c_int, POINTER(c_int)]),
+    "rir_profile_scan_pause": (c_int, [c_int]),
     "rir_profile_timeline": (c_int, [c_void_p, c_int]),
     "rir_rescore_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -154,6 +154,7 @@ using namespace rir;
 // (nq > 4096) are measured completely.
 struct ScanEventPool {
   bool armed = false;
+  bool paused = false;          // armed but not recording (sampled profiling: rir_profile_scan_pause)
   std::vector<cudaEvent_t> ev;  // pairs: ev[2i] start, ev[2i+1] stop
   size_t used = 0;              // events handed out since rir_profile_scan_begin
 };
@@ -161,7 +162,7 @@ static thread_local ScanEventPool g_scan_ev;
 
 static cudaEvent_t scan_event_next() {
   ScanEventPool& P = g_scan_ev;
-  if (!P.armed) return nullptr;
+  if (!P.armed || P.paused) return nullptr;
   if (P.used == P.ev.size()) {
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess) {
@@ -175,7 +176,13 @@ static cudaEvent_t scan_event_next() {
 
 extern "C" int rir_profile_scan_begin(void) {
   g_scan_ev.armed = true;
+  g_scan_ev.paused = false;
   g_scan_ev.used = 0;
+  return RIR_OK;
+}
+
+extern "C" int rir_profile_scan_pause(int paused) {
+  g_scan_ev.paused = paused != 0;
   return RIR_OK;
 }
 
@@ -443,7 +450,7 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
         done = true;
       } else if (e != RIR_E_NOFUSE) {
         return e;
-      } else if (g_scan_ev.armed && g_scan_ev.used > 0) {
+      } else if (g_scan_ev.armed && !g_scan_ev.paused && g_scan_ev.used > 0) {
         --g_scan_ev.used;  // the cooperative launch was refused: take the three-launch route below
       }
     }
