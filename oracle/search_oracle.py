@@ -109,3 +109,18 @@ def indices_match_up_to_ties(got_idx, got_sc, ref_idx, ref_sc, rel_eps: float, a
         if abs(a - b) > tol:
             return False, f"query {r} position {j}: got idx {got_idx[r, j]} (score {a}) vs oracle {ref_idx[r, j]} (score {b})"
     return True, f"{len(bad)} tie swaps"
+
+
+def count_outranking(shard_scores: np.ndarray, idx_offset: int, ids, id_scores) -> np.ndarray:
+    """Shard-local part of the count-based position (restates csrc/rank_positions.cu): given one query's
+    scores of THIS shard's rows and the GLOBAL scores of its ground-truth ids, the number of shard rows that outrank
+    each id in the order "score descending, ties -> lower global index".  Summed over the shards this is the id's
+    position in the full ranking, i.e. what `np.arange(N)[np.in1d(ranks[:, i], ids)]` (utils/evaluate.py:76-80) reads
+    off a complete np.argsort (iris_evaluate.py:386).  Row and id scores must come from the SAME arithmetic (a row
+    must score exactly like its own threshold, or it would count itself)."""
+    s = np.asarray(shard_scores)
+    rows = np.arange(s.shape[0], dtype=np.int64) + int(idx_offset)
+    out = np.zeros(len(ids), dtype=np.int64)
+    for j, (p, sp) in enumerate(zip(ids, id_scores)):
+        out[j] = int(np.sum((s > sp) | ((s == sp) & (rows < int(p)))))
+    return out

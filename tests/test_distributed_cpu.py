@@ -55,3 +55,45 @@ def test_short_last_shard_world2(tmp_path):
     want_s, want_i = S.topk(Q, X, k)
     z = np.load(tmp_path / "r1.npz")
     np.testing.assert_array_equal(z["mi"], want_i)
+
+
+def _count_worker(rank, world, port, n, out_dir):
+    """Count-based positions over row shards: local counts (oracle) -> all-reduce(SUM) over gloo == positions in the
+    full ranking."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Q, X, _ = synth.retrieval_set(3, n, 32, seed=91)
+        X[5] = X[700]                                           # an exact tie between two ground-truth rows
+        ids = np.array([5, 700, 33, n - 1, 901], dtype=np.int64)
+        lo, hi = search.shard_bounds(n, world, rank)
+        sim = S.similarity(Q, X)[:, lo:hi]                      # this shard's scores (one arithmetic for rows AND ids)
+        # scores of the ids: taken by the shard that owns the row, all-reduced (exactly one owner per id)
+        sc = torch.zeros(3, len(ids))
+        for j, p in enumerate(ids):
+            if lo <= p < hi:
+                sc[:, j] = sim[:, p - lo]
+        dist.all_reduce(sc)
+        cnt = torch.zeros(3, len(ids), dtype=torch.int64)
+        for qi in range(3):
+            cnt[qi] = torch.from_numpy(S.count_outranking(sim[qi].numpy(), lo, ids, sc[qi].numpy()))
+        dist.all_reduce(cnt)
+        np.savez(os.path.join(out_dir, f"c{rank}.npz"), pos=cnt.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_count_based_positions_world2(tmp_path):
+    n, world = 1203, 2
+    mp.spawn(_count_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    Q, X, _ = synth.retrieval_set(3, n, 32, seed=91)
+    X[5] = X[700]
+    ids = np.array([5, 700, 33, n - 1, 901], dtype=np.int64)
+    ranks = S.full_rank(Q, X)                                    # [nq, n], ties -> lower index
+    for r in range(world):
+        pos = np.load(tmp_path / f"c{r}.npz")["pos"]
+        for qi in range(3):
+            where = {int(v): j for j, v in enumerate(ranks[qi])}
+            assert [where[int(p)] for p in ids] == pos[qi].tolist()
+    assert abs(int(pos[0][0]) - int(pos[0][1])) == 1 and pos[0][0] < pos[0][1]   # the tie: row 5 right before row 700

@@ -144,3 +144,11 @@ def test_formats_gnd_loader_and_descriptor_store(tmp_path):
     assert torch.equal(got, q8[10:45]) and torch.equal(sc, sc8[10:45])
     with pytest.raises(ValueError):
         s8.append(q8[:5])
+
+
+def test_iris_evaluate_unknown_dataset_needs_no_gpu(capsys):
+    """iris_evaluate.py:263-265 — unknown dataset names print a message and return (None, None, None)."""
+    from research_image_retrieval_b200 import iris_evaluate as IE
+    out = IE.compute_map_and_print("holidays", "x", "global", np.zeros((3, 2), dtype=np.int64), [{}, {}])
+    assert out == (None, None, None)
+    assert capsys.readouterr().out == "Unknown dataset: holidays\n"
