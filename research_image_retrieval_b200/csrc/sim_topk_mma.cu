@@ -96,18 +96,17 @@ struct MmaGeom {
   int debug;          // development only (RIR_MMA_DEBUG): bit0 = skip the MMAs, bit1 = skip the epilogue (timing
                       // decomposition of mainloop vs epilogue; results are garbage)
   // Range mode (fused scan of one query block): CTA b owns the CONTIGUOUS rows [b * range_rows, (b + 1) * range_rows)
-  // and walks them as tiles of h_first, 256, ..., 256, h_last rows — every CTA streams the same number of bytes, so
-  // the last round is as full as the others (148 CTAs x 3.32 tiles used to run as 4 rounds with the last one 32 %
-  // occupied and HBM under-subscribed).  The ragged tile (h < 256) goes through its own tensor map (box = h rows) and
-  // an N = h tcgen05.mma.  0 = classic mode (tiles dealt round-robin).
-  int range_rows, h_first, h_last;
+  // and walks them as tiles of h_main, ..., h_main, h_last rows (both multiples of 32, <= 256) — every CTA streams the
+  // same number of bytes, so the last round is as full as the others (148 CTAs x 3.32 tiles used to run as 4 rounds
+  // with the last one 32 % occupied and HBM under-subscribed).  Each height has its tensor map (box = h rows) and its
+  // N = h tcgen05.mma.  0 = classic mode (256-row tiles dealt round-robin).
+  int range_rows, h_main, h_last;
 };
 
 // range mode: rows and height of CTA b's tile in round rd
 __device__ __forceinline__ void range_tile(const MmaGeom& g, int b, long long rd, long long* row0, int* h) {
-  const long long off = rd == 0 ? 0 : (long long)g.h_first + (rd - 1) * 256;
-  *row0 = (long long)b * g.range_rows + off;
-  *h = rd == 0 ? g.h_first : (rd == g.rounds - 1 ? g.h_last : 256);
+  *row0 = (long long)b * g.range_rows + rd * g.h_main;
+  *h = rd == g.rounds - 1 ? g.h_last : g.h_main;
 }
 
 enum { kShareNone = 0, kShareQ = 1, kShareX = 2 };
@@ -370,7 +369,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             mbar_wait(&tail->empty_b[s], ph ^ 1u);
             if (kc == 0) tl_mark(p, 1, rd);
             mbar_expect_tx(&tail->full_b[s], (uint32_t)(h * 128));
-            tma_tensor2d_g2s(ring_b + (size_t)s * kBSlot, h == kTileN ? &tmX : &tmXr, kc * kElemsPerChunk, (int)r0,
+            tma_tensor2d_g2s(ring_b + (size_t)s * kBSlot, rd == g.rounds - 1 ? &tmXr : &tmX, kc * kElemsPerChunk, (int)r0,
                              &tail->full_b[s], pol_x);
             if (++s == g.nb) { s = 0; ph ^= 1u; }
           }
@@ -1166,9 +1165,8 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     p.perm_mul = mul;
   }
   // Range mode (see MmaGeom): one query block, no CTA pairs — every CTA streams its own contiguous rows.
-  g.range_rows = g.h_first = g.h_last = 0;
+  g.range_rows = g.h_main = g.h_last = 0;
   p.range_rows = p.first_rows = 0;
-  int ragged = 0;  // height of the one tile per CTA that is not 256 rows (0: none)
   if (g.fused && g.nsb == 1 && !two && g.tile_n == kTileN && env_int("RIR_MMA_RANGE", 1) != 0) {
     long long R = (p.n + grid - 1) / grid;
     R = (R + 31) / 32 * 32;
@@ -1178,34 +1176,33 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
       R += 64 - t;
       t = 64;
     }
-    const int full = (int)((R - t) / kTileN);  // >= 1: the fused scan needs >= 2 tiles per CTA
-    // Which tile is the sample?  The ragged one first means a smaller sample but thresholds that are known before the
-    // first full tile has streamed in (no stall of the accumulator ring); it must still keep the candidate lists
-    // short: expected survivors per query ~ k * R / h_first.
-    // Measured (70 queries, 125,916-row shard): ragged tile first 98.3 us — its first-phase epilogue cannot use the
-    // unit-maxima pre-pass (fewer than 8 units) and takes as long as a full tile's — ragged tile LAST 95.7 us (the
-    // un-overlapped final epilogue covers 96 columns instead of 256), classic round-robin 98.3 us.  Default: last.
-    int tail_first = 0;
-    {
-      const int o = env_int("RIR_MMA_SAMPLE_TAIL", -1);  // tuning override (development only)
-      if (o == 1 && t >= 64 && (long long)p.k * R / t <= 4000) tail_first = 1;
+    const int rounds = (int)((R - t) / kTileN) + 1;  // >= 2: the fused scan needs >= 2 tiles per CTA
+    // Tile heights.  256, ..., 256, t leaves a short last tile whose k-chunks are small: with 4 ring slots in flight
+    // that round moves 12 KB instead of 32 KB per slot and runs latency-bound (measured on a 125,916-row shard: 14 us
+    // for 0.38 of a tile).  Spreading the rows evenly — h_main = R / rounds rounded up to 32, the last tile takes the
+    // rest — keeps every chunk near full size (864 rows: 224, 224, 224, 192 instead of 256, 256, 256, 96).
+    int h_main = (int)(((R + rounds - 1) / rounds + 31) / 32 * 32);
+    if (h_main > kTileN) h_main = kTileN;
+    int h_last = (int)(R - (long long)h_main * (rounds - 1));
+    if (h_last < 64 || env_int("RIR_MMA_EVEN_TILES", 1) == 0) {
+      h_main = kTileN;
+      h_last = t;
     }
-    if (full >= 1 && R * (long long)grid < (1ll << 31)) {
+    if (rounds >= 2 && R * (long long)grid < (1ll << 31)) {
       g.range_rows = (int)R;
-      g.h_first = tail_first ? t : kTileN;
-      g.h_last = tail_first ? kTileN : t;
-      g.rounds = full + 1;
-      ragged = t == kTileN ? 0 : t;
+      g.h_main = h_main;
+      g.h_last = h_last;
+      g.rounds = rounds;
       p.range_rows = (int)R;
-      p.first_rows = g.h_first;
+      p.first_rows = h_main;
     }
   }
   CUtensorMap tmQ, tmX, tmXr;
   if (int e = make_rowmajor_map(&tmQ, p.Q, p.nq, p.d, dtype, two ? g.a_rows / g.npairs : g.a_rows / ca)) return e;
-  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, g.tile_n / cb)) return e;
+  if (int e = make_rowmajor_map(&tmX, p.X, p.n, p.d, dtype, g.range_rows > 0 ? g.h_main : g.tile_n / cb)) return e;
   tmXr = tmX;
-  if (ragged > 0)
-    if (int e = make_rowmajor_map(&tmXr, p.X, p.n, p.d, dtype, ragged)) return e;
+  if (g.range_rows > 0 && g.h_last != g.h_main)
+    if (int e = make_rowmajor_map(&tmXr, p.X, p.n, p.d, dtype, g.h_last)) return e;
   if (dtype == RIR_BF16) return launch_mma_d<RIR_BF16>(p, g, tmQ, tmX, tmXr, grid, mb, two, st);
   return launch_mma_d<RIR_FP8E4M3>(p, g, tmQ, tmX, tmXr, grid, mb, two, st);
 }
