@@ -1184,7 +1184,7 @@ int launch_sim_mma(SimParams& p, int dtype, cudaStream_t st) {
     int h_main = (int)(((R + rounds - 1) / rounds + 31) / 32 * 32);
     if (h_main > kTileN) h_main = kTileN;
     int h_last = (int)(R - (long long)h_main * (rounds - 1));
-    if (h_last < 64 || env_int("RIR_MMA_EVEN_TILES", 1) == 0) {
+    if (h_last < 64 || env_int("RIR_MMA_EVEN_TILES", 0) == 0) {  // (opt-in until measured on the GPU)
       h_main = kTileN;
       h_last = t;
     }
