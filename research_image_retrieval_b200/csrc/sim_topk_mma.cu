@@ -19,6 +19,11 @@
 //            is not overlapped) — used from 2048 queries.
 // What bounds the tensor regime (measured on B200): the bytes each SM ingests per flop — a 128x256 tile
 // needs 48 KB per 512 MMA clocks (33% of the tensor pipe), a CTA pair 32 KB (52%), a pair with MB = 2 48 KB per 1024.
+// Tried for the two-block shape (round 2): splitting its un-overlapped 512-column epilogue over twice the warps (two
+// threads per query, half the columns each; 640 threads cap the kernel at 96 registers, small spills) — parity green
+// but SLOWER: 1024 queries 1240 -> 1153 TFLOP/s, 2048: 1307 -> 1231, 4096: 1194 -> 1213, fp8 2028 -> 1899.  With the
+// epilogue switched off the shape reaches 1545 TFLOP/s (95 % of burst): the dead time is TMEM-read / survivor bound,
+// not issue-slot bound per warp.
 // For single-block batches the query box is trimmed to the real number of queries.
 //
 // Thread-block clusters of 2:
