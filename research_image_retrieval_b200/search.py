@@ -488,7 +488,7 @@ class ShardedDatabase:
 
         def sync():
             with torch.cuda.device(dev):
-                _lib.check(lib.rir_exchange_sync(inbox, epoch))
+                _lib.check(lib.rir_exchange_sync(inbox, epoch, _lib.stream_ptr()))
         return join, sync
 
     def search_async(self, q_rows, q_scale, k: int, path: str = "auto", out=None) -> PendingQuery:
