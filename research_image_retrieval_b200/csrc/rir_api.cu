@@ -255,8 +255,13 @@ struct AsyncExchange {
   int nq;
   float* out_score;
   int32_t* out_idx;
-  cudaEvent_t merged[2];     // recorded behind the kernel that merged the epoch of parity b
+  // the merge of the epoch of parity b has been launched on merged_stream[b]; an event behind it is recorded only
+  // when somebody on ANOTHER stream (or the host) asks — an event record per step between the select kernel and the next
+  // scan would cost a few microseconds and break their programmatic-dependent-launch overlap
+  cudaEvent_t merged[2];
   uint32_t merged_epoch[2];  // which epoch that was (0 = none yet)
+  cudaStream_t merged_stream[2];
+  bool merged_recorded[2];
 };
 static std::mutex g_ax_mu;
 static std::vector<AsyncExchange*> g_ax;
@@ -273,6 +278,7 @@ static AsyncExchange* ax_find(const void* inbox, bool create) {
   a->dev = dev;
   a->pending = false;
   a->merged_epoch[0] = a->merged_epoch[1] = 0u;
+  a->merged_recorded[0] = a->merged_recorded[1] = false;
   bool ok = true;
   for (int b = 0; b < 2 && ok; ++b) ok = cudaEventCreateWithFlags(&a->merged[b], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
@@ -301,9 +307,23 @@ static int ax_flush(AsyncExchange* a, cudaStream_t st) {
   if (a == nullptr || !a->pending) return RIR_OK;
   const int b = (int)(a->ex.epoch & 1u);
   if (int e = launch_merge_exchange(a->ex, a->nq, a->ex.k_push, a->out_score, a->out_idx, st)) return e;
-  RIR_CUDA_OK(cudaEventRecord(a->merged[b], st));
   a->merged_epoch[b] = a->ex.epoch;
+  a->merged_stream[b] = st;
+  a->merged_recorded[b] = false;
   a->pending = false;
+  return RIR_OK;
+}
+
+// make `st` (or, with host = true, the calling thread) wait for the merge of parity b
+static int ax_wait_merged(AsyncExchange* a, int b, cudaStream_t st, bool host) {
+  if (!host && a->merged_stream[b] == st) return RIR_OK;  // same stream: already ordered
+  if (!a->merged_recorded[b]) {
+    // recorded late: it also covers whatever was enqueued on that stream since (conservative, never too early)
+    RIR_CUDA_OK(cudaEventRecord(a->merged[b], a->merged_stream[b]));
+    a->merged_recorded[b] = true;
+  }
+  if (host) RIR_CUDA_OK(cudaEventSynchronize(a->merged[b]));
+  else RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merged[b], 0));
   return RIR_OK;
 }
 
@@ -316,8 +336,7 @@ static int wait_previous_async_merge(const Exchange& ex, cudaStream_t st) {
   AsyncExchange* a = ax_find(ex.inbox[ex.rank], false);
   if (a == nullptr) return RIR_OK;
   const int pb = (int)((ex.epoch - 1u) & 1u);
-  if (a->merged_epoch[pb] != 0u && a->merged_epoch[pb] + 1u == ex.epoch)
-    RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merged[pb], 0));
+  if (a->merged_epoch[pb] != 0u && a->merged_epoch[pb] + 1u == ex.epoch) return ax_wait_merged(a, pb, st, false);
   return RIR_OK;
 }
 
@@ -531,8 +550,9 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
   // sharded: every rank's lists are on their way into the inboxes; wait for all G of them and merge
   if (prev.epoch != 0u) {  // the select kernel above merged the previous search
     const int pb = (int)(prev.epoch & 1u);
-    RIR_CUDA_OK(cudaEventRecord(ax->merged[pb], st));
     ax->merged_epoch[pb] = prev.epoch;
+    ax->merged_stream[pb] = st;
+    ax->merged_recorded[pb] = false;
     ax->pending = false;
   }
   if (ex_async) {
@@ -590,9 +610,7 @@ static int exchange_wait(const void* own_inbox, uint32_t epoch, cudaStream_t st,
   }
   RIR_REQUIRE(a->merged_epoch[b] == epoch, "exchange_join: epoch %u is not outstanding (parity holds %u)", epoch,
               a->merged_epoch[b]);
-  if (host) RIR_CUDA_OK(cudaEventSynchronize(a->merged[b]));
-  else RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merged[b], 0));
-  return RIR_OK;
+  return ax_wait_merged(a, b, st, host);
 }
 
 extern "C" int rir_exchange_join(const void* own_inbox, uint32_t epoch, void* stream) {
