@@ -335,30 +335,25 @@ def run_ours(args):
         peer_or_single = world == 1 or exchange.startswith("nvlink")
 
         res_out2 = (torch.empty_like(res_out[0]), torch.empty_like(res_out[1]))
-        state = {"i": 0, "prev": 0}
+        state = {"i": 0, "prev": None}
         async_exchange = world > 1 and exchange.startswith("nvlink") and not args.sync_exchange
-        # every argument of the C call bound once (SearchPlan): at 8-way sharding a step is ~0.1 ms of device time and
-        # the generic Python wrappers would spend a comparable time on the host
-        plan = rir.SearchPlan(sdb, nq, k, path=args.path) if peer_or_single else None
 
         def step_resident():
             if async_exchange:
-                # the merge of step i is deferred to the head of step i+1's select kernel; this stream joins the result
-                # of step i-1 (consumed now) — every step's result is joined before the loop moves on
-                epoch = plan.run_async(qr, qs, res_out if state["i"] & 1 == 0 else res_out2)
+                # the merge of step i runs on the exchange's side stream next to the scan of step i+1; this stream
+                # waits for the merge of step i-1 (its results are consumed now) — every step's result is joined
+                h = sdb.search_async(qr, qs, k, path=args.path, out=res_out if state["i"] & 1 == 0 else res_out2)
                 state["i"] += 1
-                if state["prev"]:
-                    plan.join(state["prev"])
-                state["prev"] = epoch
-                return epoch
-            if plan is not None:
-                return plan.run(qr, qs, res_out)
-            return sdb.search(qr, qs, k, path=args.path)
+                if state["prev"] is not None:
+                    state["prev"].wait()
+                state["prev"] = h
+                return h
+            return sdb.search(qr, qs, k, path=args.path, out=res_out if peer_or_single else None)
 
         def drain_resident():
-            if state["prev"]:
-                plan.join(state["prev"])
-                state["prev"] = 0
+            if state["prev"] is not None:
+                state["prev"].wait()
+                state["prev"] = None
 
         def step_e2e():
             if host_call:  # ONE C-ABI call on host buffers (rir_search_host) + a stream synchronise
@@ -534,9 +529,7 @@ def run_ours(args):
         nqc = min(8, args.nq)
         qr, qs = head["qr"], head["qs"]
         if world > 1 and exchange.startswith("nvlink") and not args.sync_exchange:
-            pplan = rir.SearchPlan(sdb, args.nq, k, path=args.path)           # the path that was timed
-            sc_p, ix_p = torch.empty((args.nq, k), dtype=torch.float32, device=dev), torch.empty((args.nq, k), dtype=torch.int32, device=dev)
-            pplan.join(pplan.run_async(qr, qs, (sc_p, ix_p)))
+            sc_p, ix_p = sdb.search_async(qr, qs, k, path=args.path).wait()   # the path that was timed
             sc_s, ix_s = sdb.search(qr, qs, k, path=args.path)                # and the in-stream-order flavour of it
             assert torch.equal(ix_p, ix_s) and torch.equal(sc_p, sc_s), "asynchronous exchange != synchronous exchange"
         else:

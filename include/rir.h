@@ -59,12 +59,10 @@ extern "C" {
  * issues no memset launches (its select kernel leaves the header initialised for the next call). */
 #define RIR_WS_CLEAN 0x100
 /* flag, OR-ed into `path` of rir_sim_topk_sharded: ASYNCHRONOUS exchange.  Scan and select (which publishes this
- * rank's lists) run on `stream` and the call returns; the merge that needs the PEERS' lists is deferred — it runs at the
- * head of the next asynchronous search's select kernel (same nq and k), or as its own kernel when the result is joined
- * or the shape changes — so the caller's stream goes straight on to the next search and neither the exchange latency
- * nor the skew between ranks is waited for.  out_score / out_idx are valid once rir_exchange_join (stream order) or
- * rir_exchange_sync (host) has been called for the call's epoch; at most two searches may be outstanding per inbox
- * (distinct outputs, which must stay alive until joined). */
+ * rank's lists) run on `stream`; the merge that waits for the peers' lists runs on a library-owned side stream, so the
+ * caller's stream goes straight on to the next search and the exchange latency (and the skew between ranks) hides
+ * under that search's scan.  out_score / out_idx are valid once rir_exchange_join (stream order) or rir_exchange_sync
+ * (host) has been called for the call's epoch; at most two searches may be outstanding per inbox (distinct outputs). */
 #define RIR_EXCHANGE_ASYNC 0x200
 
 /* per-(protocol,query) status written by rir_revisited_map / rir_compute_map */
@@ -228,10 +226,9 @@ int rir_sim_topk_sharded(const void* Q, const void* X, int dtype, const float* q
                          void* workspace, size_t workspace_bytes, int path, void* stream, int G, int rank,
                          uint32_t epoch, int nq_max, int k_max, void* const* inbox /* host array [G] */);
 /* RIR_EXCHANGE_ASYNC: make `stream` (join) or the host (sync) wait for the merge of the search issued with `epoch` on
- * the inbox `own_inbox` (= inbox[rank]); if no later search has taken the merge over yet it is launched now, on
- * `stream`.  No-ops when no asynchronous search was issued on that inbox. */
+ * the inbox `own_inbox` (= inbox[rank]).  No-ops when no asynchronous search was issued on that inbox. */
 int rir_exchange_join(const void* own_inbox, uint32_t epoch, void* stream);
-int rir_exchange_sync(const void* own_inbox, uint32_t epoch, void* stream);
+int rir_exchange_sync(const void* own_inbox, uint32_t epoch);
 
 /* The whole query path as one call on HOST buffers (what the reference call site holds: CPU fp32 query features,
  * iris_evaluate.py:378-386): H2D of q_host[nq,d] fp32 (pinned memory recommended) -> pack to the shard's dtype ->

@@ -13,7 +13,7 @@ from .helpfunc import extract_database, extract_vectors, extract_vectors_device,
 from .pooling import (DescriptorHead, G2Pooling, GeMPooling, MACPooling, clear_prepared_whitening, gem,  # noqa: F401
                       gem_l2_whiten, gem_pool, l2n, mac_pool, prepare_whitening, spoc, spoc_pool, ultron_gem_pooling,
                       whiten)
-from .search import (Database, HostQueryPipeline, SearchPlan, ShardedDatabase, alpha_query_expansion, merge_topk, pack_descriptors, rank,  # noqa: F401
+from .search import (Database, HostQueryPipeline, ShardedDatabase, alpha_query_expansion, merge_topk, pack_descriptors, rank,  # noqa: F401
                      rerank_topk, search_with_aqe, shard_bounds, sim_topk)
 
 from .formats import DescriptorStore, RoxfordAndRparis, gnd_to_csr  # noqa: F401

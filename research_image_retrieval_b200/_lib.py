@@ -66,7 +66,7 @@ SIGNATURES = {
                                      c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int,
                                      ctypes.c_uint32, c_int, c_int, POINTER(c_void_p)]),
     "rir_exchange_join": (c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
-    "rir_exchange_sync": (c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
+    "rir_exchange_sync": (c_int, [c_void_p, ctypes.c_uint32]),
     "rir_search_host_workspace": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
     "rir_search_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, ctypes.c_uint32, c_int, c_int,

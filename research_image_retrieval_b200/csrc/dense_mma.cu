@@ -168,10 +168,9 @@ struct DensePlan {
 
 // The tensor core accumulates in fp32 but aligns addends by truncation: a long chain of same-sign products (the
 // diagonal of a covariance over 20,000 rows: 3 x 313 chunks x 4 MMAs) drifts by ~1e-4 relative (measured).  K is
-// therefore split so that no accumulation chain exceeds kMaxChainChunks chunks (640 MMAs); the partial tiles are added
-// by the finishing kernels in IEEE fp32, in a fixed order.  (48 chunks: 1.2e-5 / 0.48 ms for 20,000 x 2048; 64: 1.5e-5 /
-// 0.47 ms; longer chains trade accuracy for fewer partial tiles to write and re-read.)
-constexpr int kMaxChainChunks = 160;
+// therefore split so that no accumulation chain exceeds kMaxChainChunks chunks; the partial tiles are added by the
+// finishing kernels in IEEE fp32, in a fixed order.
+constexpr int kMaxChainChunks = 64;
 
 static DensePlan dense_plan(long long M, long long N, long long K, bool upper_only) {
   DensePlan pl;

@@ -240,28 +240,15 @@ extern "C" int rir_sim_topk_workspace_init(void* workspace, size_t workspace_byt
 }
 
 // ---------------------------------------------------------------------------------------------
-// asynchronous exchange (RIR_EXCHANGE_ASYNC): the merge of search e is DEFERRED — it runs at the head of the select
-// kernel of search e+1 (same shape), or as a stand-alone kernel when the result is joined / the shape changes.  By
-// then the peers' lists have long arrived: neither the NVLink round trips nor the skew between ranks are waited for.
-// (A first version ran the merge on a side stream next to the following scan: the scan — a cooperative launch — then
-//  started ~11 us late on every step, 0.0950 -> 0.1063 ms at 8 GPUs, and a device-side wait for it dead-locked large
-//  batches.  Deferring needs no second stream at all.)
+// asynchronous exchange (RIR_EXCHANGE_ASYNC): per inbox, a side stream + events so that the merge of search e runs
+// next to the scan of search e+1 instead of in front of it
 // ---------------------------------------------------------------------------------------------
 struct AsyncExchange {
   const void* inbox;
   int dev;
-  bool pending;          // a search whose merge has not been launched yet
-  Exchange ex;           // its exchange descriptor (epoch, k_push, inbox table)
-  int nq;
-  float* out_score;
-  int32_t* out_idx;
-  // the merge of the epoch of parity b has been launched on merged_stream[b]; an event behind it is recorded only
-  // when somebody on ANOTHER stream (or the host) asks — an event record per step between the select kernel and the next
-  // scan would cost a few microseconds and break their programmatic-dependent-launch overlap
-  cudaEvent_t merged[2];
-  uint32_t merged_epoch[2];  // which epoch that was (0 = none yet)
-  cudaStream_t merged_stream[2];
-  bool merged_recorded[2];
+  cudaStream_t side;
+  cudaEvent_t sel_done[2], merge_done[2];
+  uint32_t epoch[2];  // epoch whose merge merge_done[b] stands for (0 = none yet)
 };
 static std::mutex g_ax_mu;
 static std::vector<AsyncExchange*> g_ax;
@@ -276,11 +263,11 @@ static AsyncExchange* ax_find(const void* inbox, bool create) {
   AsyncExchange* a = new AsyncExchange();
   a->inbox = inbox;
   a->dev = dev;
-  a->pending = false;
-  a->merged_epoch[0] = a->merged_epoch[1] = 0u;
-  a->merged_recorded[0] = a->merged_recorded[1] = false;
-  bool ok = true;
-  for (int b = 0; b < 2 && ok; ++b) ok = cudaEventCreateWithFlags(&a->merged[b], cudaEventDisableTiming) == cudaSuccess;
+  a->epoch[0] = a->epoch[1] = 0u;
+  bool ok = cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&a->sel_done[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&a->merge_done[b], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     delete a;
@@ -295,48 +282,28 @@ static void ax_drop(const void* inbox) {
   for (size_t i = 0; i < g_ax.size(); ++i)
     if (g_ax[i]->inbox == inbox) {
       AsyncExchange* a = g_ax[i];
-      for (int b = 0; b < 2; ++b) cudaEventDestroy(a->merged[b]);
+      cudaStreamSynchronize(a->side);
+      for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(a->sel_done[b]);
+        cudaEventDestroy(a->merge_done[b]);
+      }
+      cudaStreamDestroy(a->side);
       delete a;
       g_ax.erase(g_ax.begin() + i);
       return;
     }
 }
 
-// launch the deferred merge of `a` as its own kernel on `st` and remember the event behind it
-static int ax_flush(AsyncExchange* a, cudaStream_t st) {
-  if (a == nullptr || !a->pending) return RIR_OK;
-  const int b = (int)(a->ex.epoch & 1u);
-  if (int e = launch_merge_exchange(a->ex, a->nq, a->ex.k_push, a->out_score, a->out_idx, st)) return e;
-  a->merged_epoch[b] = a->ex.epoch;
-  a->merged_stream[b] = st;
-  a->merged_recorded[b] = false;
-  a->pending = false;
-  return RIR_OK;
-}
-
-// make `st` (or, with host = true, the calling thread) wait for the merge of parity b
-static int ax_wait_merged(AsyncExchange* a, int b, cudaStream_t st, bool host) {
-  if (!host && a->merged_stream[b] == st) return RIR_OK;  // same stream: already ordered
-  if (!a->merged_recorded[b]) {
-    // recorded late: it also covers whatever was enqueued on that stream since (conservative, never too early)
-    RIR_CUDA_OK(cudaEventRecord(a->merged[b], a->merged_stream[b]));
-    a->merged_recorded[b] = true;
-  }
-  if (host) RIR_CUDA_OK(cudaEventSynchronize(a->merged[b]));
-  else RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merged[b], 0));
-  return RIR_OK;
-}
-
 // A rank may only PUBLISH epoch e (its select kernel stores into the peers' inboxes) once its own merge of epoch e-1 has
 // read every list: a peer needs this rank's epoch-e lists before it can move on to epoch e+1 and overwrite inbox rows of
-// parity (e-1) & 1.  A merge folded into this search's select kernel keeps that order per query (the CTA merges query
-// q of e-1, then publishes query q of e); a merge that ran as its own kernel — possibly on another stream, through
-// rir_exchange_join — is waited for here, by the stream.
+// parity (e-1) & 1.  With the merge in stream order that holds by itself; a merge on the side stream is waited for
+// HERE, by the stream (between scan and select: the scan still overlaps it) — not by spinning CTAs, which would hold
+// the SM resources the merge kernel needs (a 1,024-query select fills the register files: measured dead-lock).
 static int wait_previous_async_merge(const Exchange& ex, cudaStream_t st) {
   AsyncExchange* a = ax_find(ex.inbox[ex.rank], false);
   if (a == nullptr) return RIR_OK;
   const int pb = (int)((ex.epoch - 1u) & 1u);
-  if (a->merged_epoch[pb] != 0u && a->merged_epoch[pb] + 1u == ex.epoch) return ax_wait_merged(a, pb, st, false);
+  if (a->epoch[pb] != 0u && a->epoch[pb] + 1u == ex.epoch) RIR_CUDA_OK(cudaStreamWaitEvent(st, a->merge_done[pb], 0));
   return RIR_OK;
 }
 
@@ -389,10 +356,8 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     p.Q = Q; p.X = X; p.q_scale = q_scale; p.x_scale = x_scale;
     p.nq = nq; p.q0 = 0; p.n = n_local; p.d = d; p.row_bytes = d * esz;
     if (ex) p.ex = *ex;
-    if (ex) {
-      if (int e = ax_flush(ax_find(ex->inbox[ex->rank], false), st)) return e;
+    if (ex)
       if (int e = wait_previous_async_merge(*ex, st)) return e;
-    }
     if (int e = launch_exact_scan(p, dtype, nq, k, idx_offset, out_score, out_idx, nullptr, st)) return e;
     if (ex) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
     return RIR_OK;
@@ -406,26 +371,6 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   // one query group whose select CTAs are all co-resident: the select kernel merges the peers' lists itself
   if (ex && !ex_async && nq <= pl.group && select_can_fold_merge(nq, ex->G, k_req)) exl.fold = 1;
-  // A deferred merge of the previous (asynchronous) search: the head of THIS search's select kernel takes it over when
-  // the shapes agree (CTA q merges query q of the previous epoch, then selects and publishes query q of this one);
-  // otherwise it runs now, as its own kernel in front of the scan.
-  PrevMerge prev{};
-  AsyncExchange* ax = ex ? ax_find(ex->inbox[ex->rank], ex_async) : nullptr;
-  if (ex_async && ax == nullptr) {
-    set_error("sim_topk_sharded: could not create the events of the asynchronous exchange");
-    return RIR_E_CUDA;
-  }
-  if (ax != nullptr && ax->pending) {
-    const bool takeover = ex_async && ax->ex.epoch + 1u == ex->epoch && ax->nq == nq && ax->ex.k_push == k_req &&
-                          nq <= pl.group && select_can_fold_merge(nq, ex->G, k_req);
-    if (takeover) {
-      prev.epoch = ax->ex.epoch;
-      prev.out_score = ax->out_score;
-      prev.out_idx = ax->out_idx;
-    } else if (int e = ax_flush(ax, st)) {
-      return e;
-    }
-  }
 
   for (int g0 = 0; g0 < nq; g0 += pl.group) {
     const int gq = (nq - g0) < pl.group ? (nq - g0) : pl.group;
@@ -540,7 +485,6 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     int32_t* oi = out_idx + (size_t)g0 * k;
     if (ex && g0 == 0)
       if (int e = wait_previous_async_merge(*ex, st)) return e;
-    p.prev = prev;
     if (int e = launch_final_select(p, dtype, gq, k, idx_offset, os, oi, ovf, st)) return e;
     if (!pl.scan_all && !select_handles_overflow(k)) {
       // very large k: queries whose candidate list overflowed are redone by the separate exact kernel (no-op otherwise)
@@ -548,21 +492,20 @@ static int sim_topk_impl(const void* Q, const void* X, int dtype, const float* q
     }
   }
   // sharded: every rank's lists are on their way into the inboxes; wait for all G of them and merge
-  if (prev.epoch != 0u) {  // the select kernel above merged the previous search
-    const int pb = (int)(prev.epoch & 1u);
-    ax->merged_epoch[pb] = prev.epoch;
-    ax->merged_stream[pb] = st;
-    ax->merged_recorded[pb] = false;
-    ax->pending = false;
-  }
   if (ex_async) {
-    // this search's merge is deferred: remember what it needs (the next search's select kernel, rir_exchange_join or
-    // rir_exchange_sync runs it); the caller's stream goes straight on
-    ax->pending = true;
-    ax->ex = *ex;
-    ax->nq = nq;
-    ax->out_score = out_score;
-    ax->out_idx = out_idx;
+    // on the inbox's side stream, behind this call's select kernels: the caller's stream goes straight on to the next
+    // search; rir_exchange_join / rir_exchange_sync order consumers behind the merge
+    AsyncExchange* a = ax_find(ex->inbox[ex->rank], true);
+    if (a == nullptr) {
+      set_error("sim_topk_sharded: could not create the side stream of the asynchronous exchange");
+      return RIR_E_CUDA;
+    }
+    const int b = (int)(ex->epoch & 1u);
+    RIR_CUDA_OK(cudaEventRecord(a->sel_done[b], st));
+    RIR_CUDA_OK(cudaStreamWaitEvent(a->side, a->sel_done[b], 0));
+    if (int e = launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, a->side, true)) return e;
+    RIR_CUDA_OK(cudaEventRecord(a->merge_done[b], a->side));
+    a->epoch[b] = ex->epoch;
     return RIR_OK;
   }
   if (ex && !ex->fold) return launch_merge_exchange(*ex, nq, k_req, out_score, out_idx, st);
@@ -601,24 +544,22 @@ extern "C" int rir_peer_free(void* ptr) {
   return RIR_OK;
 }
 
-static int exchange_wait(const void* own_inbox, uint32_t epoch, cudaStream_t st, bool host) {
+extern "C" int rir_exchange_join(const void* own_inbox, uint32_t epoch, void* stream) {
   AsyncExchange* a = ax_find(own_inbox, false);
   if (a == nullptr) return RIR_OK;  // no asynchronous search was issued on this inbox
   const int b = (int)(epoch & 1u);
-  if (a->pending && a->ex.epoch == epoch) {  // nobody has merged it yet: do it now, on this stream
-    if (int e = ax_flush(a, st)) return e;
-  }
-  RIR_REQUIRE(a->merged_epoch[b] == epoch, "exchange_join: epoch %u is not outstanding (parity holds %u)", epoch,
-              a->merged_epoch[b]);
-  return ax_wait_merged(a, b, st, host);
+  RIR_REQUIRE(a->epoch[b] == epoch, "exchange_join: epoch %u is not outstanding (parity holds %u)", epoch, a->epoch[b]);
+  RIR_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, a->merge_done[b], 0));
+  return RIR_OK;
 }
 
-extern "C" int rir_exchange_join(const void* own_inbox, uint32_t epoch, void* stream) {
-  return exchange_wait(own_inbox, epoch, (cudaStream_t)stream, false);
-}
-
-extern "C" int rir_exchange_sync(const void* own_inbox, uint32_t epoch, void* stream) {
-  return exchange_wait(own_inbox, epoch, (cudaStream_t)stream, true);
+extern "C" int rir_exchange_sync(const void* own_inbox, uint32_t epoch) {
+  AsyncExchange* a = ax_find(own_inbox, false);
+  if (a == nullptr) return RIR_OK;
+  const int b = (int)(epoch & 1u);
+  RIR_REQUIRE(a->epoch[b] == epoch, "exchange_sync: epoch %u is not outstanding (parity holds %u)", epoch, a->epoch[b]);
+  RIR_CUDA_OK(cudaEventSynchronize(a->merge_done[b]));
+  return RIR_OK;
 }
 
 extern "C" int rir_peer_export(void* ptr, void* handle64) {
@@ -730,9 +671,7 @@ extern "C" int rir_search_host(const float* q_host, const void* X, int dtype, co
     return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
   };
   // bit 0: queries read in place, bit 1: results written in place (development override RIR_HOST_ZERO_COPY)
-  // (measured, 70 x 2048 fp32 queries = 573 KB, 1/8 shard, one batch at a time: both in place 142.6 us per step, results
-  //  only 150.3, neither 163.6 — the pack kernel pulling the queries over PCIe beats a DMA copy + a kernel reading HBM)
-  static const int zero_copy = getenv("RIR_HOST_ZERO_COPY") ? atoi(getenv("RIR_HOST_ZERO_COPY")) : 3;
+  static const int zero_copy = getenv("RIR_HOST_ZERO_COPY") ? atoi(getenv("RIR_HOST_ZERO_COPY")) : 2;
   const float* q_dev_view =
       ((zero_copy & 1) && dtype != RIR_F32) ? reinterpret_cast<const float*>(device_view(q_host)) : nullptr;
   float* sc_dev_view = (zero_copy & 2) ? reinterpret_cast<float*>(device_view(out_score_host)) : nullptr;

@@ -59,14 +59,6 @@ __host__ __device__ __forceinline__ uint32_t* exchange_flag(unsigned long long* 
          ((size_t)b * ex.G + g) * ex.nq_max + q;
 }
 
-// deferred merge of the PREVIOUS sharded search, taken over by this search's select kernel (epoch 0 = none): same
-// inbox, rank count, nq and k as this search
-struct PrevMerge {
-  uint32_t epoch;
-  float* out_score;
-  int32_t* out_idx;
-};
-
 struct SimParams {
   const void* Q;         // [nq, d]
   const void* X;         // [n, d]
@@ -104,7 +96,6 @@ struct SimParams {
   int first_rows;        //   0 = classic mode (slot s is tile (s * perm_mul) % perm_n)
   int k;                 // top-k requested (the fused scan computes tau itself)
   Exchange ex;           // sharded search: push the local top-k to the peers instead of writing out_score / out_idx
-  PrevMerge prev;        // sharded search: the previous search's merge, done at the head of the select kernel
   // development: per-CTA event timeline of the tcgen05 scan (rir_profile_timeline); null in production
   unsigned long long* timeline;  // [0] = event counter, then (meta, globaltimer ns) pairs
   int timeline_cap;              // events that fit
@@ -139,7 +130,8 @@ int launch_final_select(const SimParams& p, int dtype, int nq_total, int k, long
                         int32_t* out_idx, uint32_t* ovf, cudaStream_t st);
 bool select_handles_overflow(int k);  // the select kernel redoes overflowed queries itself (no fallback launch needed)
 bool select_can_fold_merge(int nq_total, int G, int k_push);
-int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st);
+int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st,
+                          bool side_stream = false);
 int launch_exact_scan(const SimParams& p, int dtype, int nq_total, int k, long long idx_offset, float* out_score,
                       int32_t* out_idx, const uint32_t* ovf /*nullptr = all queries*/, cudaStream_t st);
 

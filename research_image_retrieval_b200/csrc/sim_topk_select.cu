@@ -121,12 +121,18 @@ __device__ __forceinline__ void push_sorted_to_peers(const Exchange& ex, int q, 
   }
 }
 
-// Wait until all G ranks have published query `qg` for `epoch`, merge the G sorted lists out of this rank's own inbox
-// and write the global top-k.  `lists` holds >= G * k_push keys, `mdst` >= k_push keys (shared memory).  All threads of
-// the block must call.
-__device__ __forceinline__ void wait_and_merge(const Exchange& ex, uint32_t epoch, int qg, uint64_t* lists, uint64_t* mdst,
-                                               float* out_score, int32_t* out_idx) {
-  const int b = (int)(epoch & 1u);
+// Sharded search with the merge FOLDED into the select kernel (ex.fold: every query's CTA is co-resident, i.e. at most
+// one CTA per SM): push this rank's list, wait until all G ranks have published query q for this epoch, merge the G
+// sorted lists out of this rank's own inbox and write the global top-k — no separate merge launch.  Nobody waits
+// before having pushed, and every waiting CTA is resident, so the wait cannot dead-lock.  `lists` holds >= G * k_push
+// keys, `mdst` >= k_push keys (shared memory).  All threads of the block must call.
+__device__ __forceinline__ void exchange_and_merge(const Exchange& ex, int q, const uint64_t* sorted, int got, int k,
+                                                   long long idx_offset, uint64_t* lists, uint64_t* mdst, float* out_score,
+                                                   int32_t* out_idx) {
+  push_sorted_to_peers(ex, q, sorted, got, k, idx_offset);
+  if (!ex.fold) return;
+  const int b = (int)(ex.epoch & 1u);
+  const int qg = ex.q_base + q;
   unsigned long long* mine = ex.inbox[ex.rank];
   if ((int)threadIdx.x < ex.G) {
     const uint32_t* f = exchange_flag(mine, ex, b, threadIdx.x, qg);
@@ -134,11 +140,11 @@ __device__ __forceinline__ void wait_and_merge(const Exchange& ex, uint32_t epoc
     while (true) {
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (v == epoch) break;
+      if (v == ex.epoch) break;
       __nanosleep(100);
       if (clock64() - t0 > 20000000000ll) {
         printf("librir: rank %d never received query %d of rank %d (epoch %u, saw %u)\n", ex.rank, qg, (int)threadIdx.x,
-               epoch, v);
+               ex.epoch, v);
         __trap();
       }
     }
@@ -152,18 +158,6 @@ __device__ __forceinline__ void wait_and_merge(const Exchange& ex, uint32_t epoc
   __syncthreads();
   block_merge_sorted_lists(lists, ex.G, kp, mdst);
   write_sorted(mdst, kp, kp, 0, out_score + (size_t)qg * kp, out_idx + (size_t)qg * kp);
-  __syncthreads();
-}
-
-// Sharded search with the merge FOLDED into the select kernel (ex.fold: every query's CTA is co-resident, i.e. at most
-// one CTA per SM): push this rank's list, then wait for the peers' and merge — no separate merge launch.  Nobody waits
-// before having pushed, and every waiting CTA is resident, so the wait cannot dead-lock.
-__device__ __forceinline__ void exchange_and_merge(const Exchange& ex, int q, const uint64_t* sorted, int got, int k,
-                                                   long long idx_offset, uint64_t* lists, uint64_t* mdst, float* out_score,
-                                                   int32_t* out_idx) {
-  push_sorted_to_peers(ex, q, sorted, got, k, idx_offset);
-  if (!ex.fold) return;
-  wait_and_merge(ex, ex.epoch, ex.q_base + q, lists, mdst, out_score, out_idx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -346,10 +340,6 @@ __global__ void __launch_bounds__(kSelectThreads)
   pdl_wait();
   pdl_launch_dependents();
   const int q = blockIdx.x;
-  // Asynchronous exchange: the PREVIOUS search's merge was deferred to here — its lists arrived while this search's
-  // scan was running, so nothing is waited for.  CTA q merges query q of that search, then selects (and publishes)
-  // query q of this one: a peer that sees this rank's new list knows the old inbox rows of that query are free.
-  if (p.prev.epoch != 0u) wait_and_merge(p.ex, p.prev.epoch, p.ex.q_base + q, stage, dst, p.prev.out_score, p.prev.out_idx);
   if (threadIdx.x == 0) {
     s_cnt = (p.mode == kModeScanAll) ? (uint32_t)p.n : __ldcg(&p.cnt[q]);  // scan-all: slot == row
     s_ts = __ldcg(&p.tau_score[q]);
@@ -627,13 +617,19 @@ __global__ void __launch_bounds__(kSelectThreads)
   write_sorted(dst, got, k, 0, out_sc + (size_t)q * k, out_ix + (size_t)q * k);
 }
 
-int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st) {
+int launch_merge_exchange(const Exchange& ex, int nq, int k, float* out_score, int32_t* out_idx, cudaStream_t st,
+                          bool side_stream) {
   const int kpad = pow2_ceil_int(k < 32 ? 32 : k);
   const int m = ex.G * k;
   const size_t smem = (size_t)(kpad + (m <= kMergeStage ? m : 0)) * sizeof(uint64_t);
   RIR_CUDA_OK(ensure_dyn_smem(merge_exchange_kernel, smem));
-  RIR_CUDA_OK(launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3((unsigned)select_threads()), smem, st, ex, k, kpad,
-                         out_score, out_idx));
+  if (side_stream) {
+    // runs next to the following search's scan (one scan CTA per SM leaves room): a small CTA, no PDL edge
+    merge_exchange_kernel<<<nq, 256, smem, st>>>(ex, k, kpad, out_score, out_idx);
+  } else {
+    RIR_CUDA_OK(launch_pdl(merge_exchange_kernel, dim3((unsigned)nq), dim3((unsigned)select_threads()), smem, st, ex, k,
+                           kpad, out_score, out_idx));
+  }
   RIR_LAUNCH_OK();
   return RIR_OK;
 }

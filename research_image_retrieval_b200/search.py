@@ -488,7 +488,7 @@ class ShardedDatabase:
 
         def sync():
             with torch.cuda.device(dev):
-                _lib.check(lib.rir_exchange_sync(inbox, epoch, _lib.stream_ptr()))
+                _lib.check(lib.rir_exchange_sync(inbox, epoch))
         return join, sync
 
     def search_async(self, q_rows, q_scale, k: int, path: str = "auto", out=None) -> PendingQuery:
@@ -571,73 +571,6 @@ class ShardedDatabase:
         return merge_topk(all_s, all_i)
 
 
-class SearchPlan:
-    """A search of fixed shape (nq, k) over a Database or ShardedDatabase with every argument of the C call bound once:
-    `run` / `run_async` cost ONE ctypes call each.  At 8-way sharding a step is ~100 us of device time; the generic
-    wrappers (tensor checks, workspace lookups, context managers, closures) spend a comparable time on the host, so a
-    serving loop uses a plan.  The caller keeps the plan's device current and passes contiguous packed queries."""
-
-    def __init__(self, db, nq: int, k: int, path: str = "auto"):
-        self.sdb = db if isinstance(db, ShardedDatabase) else None
-        loc = self.local = db.local if self.sdb is not None else db
-        self.nq, self.k = int(nq), int(k)
-        self.sharded = self.sdb is not None and self.sdb.world > 1 and self.sdb._inbox is not None
-        if self.sdb is not None and self.sdb.world > 1 and not self.sharded:
-            raise ValueError("enable_peer_exchange(nq_max, k_max) first: a plan binds the peer-memory exchange")
-        if self.sharded and (nq > self.sdb._nq_max or k > self.sdb._k_max):
-            raise ValueError("nq / k exceed the inbox (enable_peer_exchange)")
-        k_local = min(self.k, loc.n)
-        if not self.sharded and k_local != self.k:
-            raise ValueError(f"k={k} exceeds the database size {loc.n}")
-        check_k_supported(k_local, loc.n)
-        self.lib = _lib.load()
-        self.dev_index = loc.rows.device.index
-        self.ws = loc.workspace(self.nq, k_local)     # (initialised; belongs to the stream current NOW)
-        self.dt = _DTYPES[loc.dtype]
-        self.flags = PATHS[path] | RIR_WS_CLEAN
-        self.x_ptr = loc.rows.data_ptr()
-        self.xs_ptr = None if loc.scale is None else loc.scale.data_ptr()
-        self.k_local = k_local
-
-    def _call(self, q_rows, q_scale, sc, ix, stream_ptr, flags):
-        loc, lib = self.local, self.lib
-        qs_ptr = None if q_scale is None else q_scale.data_ptr()
-        if self.sharded:
-            sdb = self.sdb
-            sdb._epoch += 1
-            rc = lib.rir_sim_topk_sharded(q_rows.data_ptr(), self.x_ptr, self.dt, qs_ptr, self.xs_ptr, self.nq, loc.n, loc.d,
-                                          self.k, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), self.ws.data_ptr(),
-                                          self.ws.numel(), self.flags | flags, stream_ptr, sdb.world, sdb.rank, sdb._epoch,
-                                          sdb._nq_max, sdb._k_max, sdb._peers)
-        else:
-            rc = lib.rir_sim_topk(q_rows.data_ptr(), self.x_ptr, self.dt, qs_ptr, self.xs_ptr, self.nq, loc.n, loc.d,
-                                  self.k_local, loc.idx_offset, sc.data_ptr(), ix.data_ptr(), self.ws.data_ptr(),
-                                  self.ws.numel(), self.flags, stream_ptr)
-        if rc:
-            loc._drop_workspaces()
-            _lib.check(rc)
-
-    def run(self, q_rows, q_scale, out, stream_ptr=None):
-        """Search in stream order; `out` = (scores [nq, k] fp32, idx [nq, k] int32) tensors (device or pinned host)."""
-        self._call(q_rows, q_scale, out[0], out[1], _lib.stream_ptr() if stream_ptr is None else stream_ptr, 0)
-        return out
-
-    def run_async(self, q_rows, q_scale, out, stream_ptr=None) -> int:
-        """Sharded: asynchronous exchange (RIR_EXCHANGE_ASYNC) — returns the epoch to pass to `join` / `sync` before the
-        outputs are read.  Unsharded: same as run, returns 0."""
-        self._call(q_rows, q_scale, out[0], out[1], _lib.stream_ptr() if stream_ptr is None else stream_ptr,
-                   RIR_EXCHANGE_ASYNC if self.sharded else 0)
-        return self.sdb._epoch if self.sharded else 0
-
-    def join(self, epoch: int, stream_ptr=None) -> None:
-        if self.sharded and epoch:
-            _lib.check(self.lib.rir_exchange_join(self.sdb._inbox, epoch, _lib.stream_ptr() if stream_ptr is None else stream_ptr))
-
-    def sync(self, epoch: int, stream_ptr=None) -> None:
-        if self.sharded and epoch:
-            _lib.check(self.lib.rir_exchange_sync(self.sdb._inbox, epoch, _lib.stream_ptr() if stream_ptr is None else stream_ptr))
-
-
 class HostQueryPipeline:
     """Serving loop for host-resident query batches: `submit(q_host)` enqueues one batch and returns a PendingQuery.
 
@@ -661,7 +594,6 @@ class HostQueryPipeline:
             raise ValueError(f"k={k} exceeds the database size {loc.n}")
         self.nq, self.k, self.depth, self.path = int(nq), int(k), int(depth), path
         dev = loc.rows.device
-        self.plan = SearchPlan(db, nq, k, path)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
         for _ in range(self.depth):
@@ -671,40 +603,54 @@ class HostQueryPipeline:
                 "qs": torch.empty(nq, dtype=torch.float32, device=dev) if loc.dtype == "fp8" else None,
                 "sc": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                 "ix": torch.empty((nq, k), dtype=torch.int32).pin_memory(),
-                "copied": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False})
+                "copied": torch.cuda.Event(), "done": None})
         self._i = 0
 
     def submit(self, q_host: torch.Tensor) -> PendingQuery:
-        """(The device of the database must be current.)"""
-        loc, lib = self.local, self.plan.lib
+        loc, lib = self.local, _lib.load()
         if q_host.is_cuda or q_host.dtype != torch.float32 or tuple(q_host.shape) != (self.nq, loc.d):
             raise TypeError(f"expected a float32 CPU tensor [{self.nq}, {loc.d}] (pinned for an asynchronous copy)")
         slot = self.slots[self._i % self.depth]
         self._i += 1
-        main = torch.cuda.current_stream()
-        cs = self.copy_stream
-        if slot["used"]:
-            cs.wait_event(slot["done"])    # the search that last read this staging slot has finished
-        if q_host.is_pinned() and q_host.is_contiguous():
-            # pinned host memory is device-addressable (UVA): the pack kernel pulls the queries over PCIe itself — no
-            # separate copy operation (measured faster than DMA copy + pack at 573 KB, and one launch less)
-            src = q_host.data_ptr()
-        else:
-            with torch.cuda.stream(cs):
+        main = torch.cuda.current_stream(loc.rows.device)
+        dt = _DTYPES[loc.dtype]
+        with torch.cuda.device(loc.rows.device):
+            if slot["done"] is not None:
+                self.copy_stream.wait_event(slot["done"])    # the search that last read this staging slot has finished
+            with torch.cuda.stream(self.copy_stream):
                 slot["q32"].copy_(q_host, non_blocking=True)
-            src = slot["q32"].data_ptr()
-        _lib.check(lib.rir_pack_descriptors(src, self.nq, loc.d, self.plan.dt, slot["qr"].data_ptr(),
-                                            None if slot["qs"] is None else slot["qs"].data_ptr(), cs.cuda_stream))
-        slot["copied"].record(cs)
-        main.wait_event(slot["copied"])
-        # the select / merge kernels store the top-k straight into the pinned result buffers
-        epoch = self.plan.run_async(slot["qr"], slot["qs"], (slot["sc"], slot["ix"]), main.cuda_stream)
-        slot["done"].record(main)   # scan + select have read the staging slot (and, unsharded, written the top-k)
-        slot["used"] = True
-        join = sync = None
-        if epoch:
-            plan, sp = self.plan, main.cuda_stream
-            join, sync = (lambda: plan.join(epoch)), (lambda: plan.sync(epoch, sp))
+                _lib.check(lib.rir_pack_descriptors(slot["q32"].data_ptr(), self.nq, loc.d, dt, slot["qr"].data_ptr(),
+                                                    None if slot["qs"] is None else slot["qs"].data_ptr(),
+                                                    self.copy_stream.cuda_stream))
+                slot["copied"].record(self.copy_stream)
+            main.wait_event(slot["copied"])
+            k_local = min(self.k, loc.n)
+            check_k_supported(k_local, loc.n)
+            ws = loc.workspace(self.nq, k_local)
+            qs_ptr = None if slot["qs"] is None else slot["qs"].data_ptr()
+            xs_ptr = None if loc.scale is None else loc.scale.data_ptr()
+            join = sync = None
+            try:
+                # pinned host memory is device-addressable (UVA): the kernels store the top-k straight into it
+                if isinstance(self.db, ShardedDatabase) and self.db.world > 1:
+                    sdb = self.db
+                    sdb._epoch += 1
+                    _lib.check(lib.rir_sim_topk_sharded(
+                        slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, self.k,
+                        loc.idx_offset, slot["sc"].data_ptr(), slot["ix"].data_ptr(), ws.data_ptr(), ws.numel(),
+                        PATHS[self.path] | RIR_WS_CLEAN | RIR_EXCHANGE_ASYNC, main.cuda_stream, sdb.world, sdb.rank,
+                        sdb._epoch, sdb._nq_max, sdb._k_max, sdb._peers))
+                    join, sync = sdb._exchange_waiters(sdb._epoch, loc.rows.device)   # the merge is on the side stream
+                else:
+                    _lib.check(lib.rir_sim_topk(
+                        slot["qr"].data_ptr(), loc.rows.data_ptr(), dt, qs_ptr, xs_ptr, self.nq, loc.n, loc.d, k_local,
+                        loc.idx_offset, slot["sc"].data_ptr(), slot["ix"].data_ptr(), ws.data_ptr(), ws.numel(),
+                        PATHS[self.path] | RIR_WS_CLEAN, main.cuda_stream))
+            except _lib.RirError:
+                loc._drop_workspaces()
+                raise
+            slot["done"] = torch.cuda.Event()   # scan + select have read the staging slot (and, unsharded, written the top-k)
+            slot["done"].record(main)
         return PendingQuery(slot["done"], slot["sc"], slot["ix"], keep=q_host, join=join, sync=sync)
 
 

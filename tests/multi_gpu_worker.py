@@ -59,22 +59,6 @@ def main():
                 assert torch.equal(a_ix, want_ix) and torch.equal(a_sc, want_sc), f"case {ci} rep {rep}: async exchange differs"
         a_sc, a_ix = pend.pop(0).result()
         assert torch.equal(a_ix, want_ix) and torch.equal(a_sc, want_sc), f"case {ci}: async exchange (host sync) differs"
-        # the same through a SearchPlan (arguments bound once), join in stream order / on the host
-        plan = rir.SearchPlan(sdb, nq, min(k, n))
-        prev = 0
-        for rep in range(4):
-            ep = plan.run_async(qr, qs, outs[rep & 1])
-            if prev:
-                plan.join(prev)
-                torch.cuda.current_stream().synchronize()
-                assert torch.equal(outs[(rep - 1) & 1][1], want_ix) and torch.equal(outs[(rep - 1) & 1][0], want_sc), \
-                    f"case {ci} rep {rep}: plan.run_async differs"
-            prev = ep
-        plan.sync(prev)
-        assert torch.equal(outs[1][1], want_ix) and torch.equal(outs[1][0], want_sc), f"case {ci}: plan.sync differs"
-        plan.run(qr, qs, outs[0])
-        torch.cuda.synchronize()
-        assert torch.equal(outs[0][1], want_ix), f"case {ci}: plan.run differs"
         sc, ix = sdb.search(qr, qs, min(k, n))                       # synchronous call right behind asynchronous ones
         assert torch.equal(ix, want_ix) and torch.equal(sc, want_sc), f"case {ci}: sync after async differs"
         # a smaller batch afterwards (stale inbox rows must not leak in)

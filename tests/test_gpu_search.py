@@ -710,22 +710,3 @@ def test_rank_fp32_on_a_large_gallery(cuda_device):
     assert ok, msg
     with pytest.raises(ValueError, match="revisited_map_full"):
         rir.rank(Q, X)
-
-
-def test_search_plan_matches_generic_call(cuda_device):
-    """SearchPlan (every C-call argument bound once) == Database.search, repeatedly and into caller-owned outputs."""
-    nq, n, d, k = 70, 100003, 128, 100
-    Q, X, _ = synth.retrieval_set(2 * nq, n, d, seed=808)
-    db = rir.Database.from_descriptors(X.to(cuda_device), "fp8")
-    qr, qs = db.pack_queries(Q.to(cuda_device))
-    plan = rir.SearchPlan(db, nq, k)
-    out = (torch.empty((nq, k), dtype=torch.float32, device=cuda_device), torch.empty((nq, k), dtype=torch.int32, device=cuda_device))
-    for lo in (0, nq, 0):
-        q, s = qr[lo:lo + nq].contiguous(), qs[lo:lo + nq].contiguous()
-        want = db.search(q, s, k)
-        plan.run(q, s, out)
-        assert plan.run_async(q, s, out) == 0           # unsharded: nothing to join
-        torch.cuda.synchronize()
-        assert torch.equal(out[1], want[1]) and torch.equal(out[0], want[0])
-    with pytest.raises(ValueError):
-        rir.SearchPlan(db, nq, n + 1)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# (2 GPUs) deferred merge + SearchPlan: multi-rank tests, single-GPU suites, benches at full and 1/8-size shards
+# (2 GPUs; run on the deferred-merge variant, commit 87d3f32..35a0a04) multi-rank tests, single-GPU suites, benches at full and 1/8-size shards
 mkdir -p gpurun_out
 timeout 900 python -m pytest -x -q -m gpu tests/test_gpu_multi.py > gpurun_out/test_multi.log 2>&1; echo "test_multi rc=$?"; tail -4 gpurun_out/test_multi.log; grep -E "Error|assert" gpurun_out/multi_worker_w2.log | head -5
 bash tools/gpu_check.sh; echo "gpu_check rc=$?"

@@ -20,18 +20,17 @@ for lo in range(0, n, 65536):
 Q = torch.randn(nq, d, generator=gen, device=dev)
 Q = (Q / Q.norm(dim=1, keepdim=True)).to(torch.bfloat16)
 db = rir.Database(X, None, "bf16")
-plan = rir.SearchPlan(db, nq, k)
 out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
 
 
 def timed(label, steps=400):
     for _ in range(20):
-        plan.run(Q, None, out)
+        db.search(Q, None, k, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        plan.run(Q, None, out)
+        db.search(Q, None, k, out=out)
     e1.record()
     torch.cuda.synchronize()
     print(f"{label:46s} {e0.elapsed_time(e1) / steps * 1e3:8.1f} us/step")
