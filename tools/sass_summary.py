@@ -33,15 +33,30 @@ def main():
             kernels[cur][op.split(".")[0]] += 1
             if op.startswith(("UTC", "UTMA", "LDTM", "UBLKCP")):
                 kernels[cur]["full:" + op] += 1
+    res = {}   # registers / static shared / local (spill) bytes per kernel: cuobjdump --dump-resource-usage
+    ru = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True, check=True).stdout
+    fn = None
+    for line in ru.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            fn = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", line)
+        if m and fn:
+            res[fn] = tuple(int(x) for x in m.groups())
+            fn = None
     demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     print(f"# cuobjdump -sass {os.path.relpath(LIB, ROOT)} (sm_100a), sources at HEAD {head} (+ working tree)")
     print("# per kernel: instruction count, then the opcodes that matter (tcgen05.mma = UTC*MMA, tcgen05.ld = LDTM,")
-    print("# TMA = UTMALDG / UBLKCP, tcgen05.commit = UTCBAR; HMMA would be a legacy mma.sync path: none expected)")
+    print("# TMA = UTMALDG / UBLKCP, tcgen05.commit = UTCBAR; HMMA would be a legacy mma.sync path: none expected);")
+    print("# regs / stack / static shared / local bytes from cuobjdump --dump-resource-usage (local > 0 = spills)")
     for (name, c), dm in zip(kernels.items(), demangle):
         short = re.sub(r"\(.*", "", dm)
         ops = " ".join(f"{k}={c[k]}" for k in WATCH if c[k])
-        print(f"\n{short}  [{c['_total']} instr]\n    {ops}")
+        r = res.get(name)
+        usage = f"  regs={r[0]} stack={r[1]} smem_static={r[2]} local={r[3]}" if r else ""
+        print(f"\n{short}  [{c['_total']} instr]{usage}\n    {ops}")
         full = sorted((k[5:], v) for k, v in c.items() if k.startswith("full:"))
         if full:
             print("    " + "  ".join(f"{k} x{v}" for k, v in full))
